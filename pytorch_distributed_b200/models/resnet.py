@@ -1,0 +1,157 @@
+"""Native ResNet family (resnet18/34/50/101/152, resnext, wide_resnet).
+
+Written from scratch; parameter / buffer names match torchvision's ResNet so the
+reference checkpoint layout (``state_dict`` of the unwrapped module,
+/root/reference/distributed.py:219-225) is interchangeable with torchvision.
+
+What is B200-specific: every BatchNorm is a :class:`BNAct` that runs the
+hand-written NHWC kernels in ``csrc/bn_act.cu`` (statistics pass + one fused
+normalise(+residual add)(+ReLU) pass, and the matching two-pass backward), so a
+bottleneck block issues 3 convs + 6 elementwise kernels instead of 3 convs + ~10.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from ..ops.bn_act import bn_act
+
+
+class BNAct(nn.BatchNorm2d):
+    """BatchNorm2d with optional fused residual add and ReLU: ``relu(bn(x) + residual)``."""
+
+    def __init__(self, num_features, relu=True, fused=None, **kw):
+        super().__init__(num_features, **kw)
+        self.relu = relu
+        self.fused = fused
+
+    def forward(self, x, residual=None):  # type: ignore[override]
+        if self.training and self.track_running_stats and self.num_batches_tracked is not None:
+            self.num_batches_tracked.add_(1)
+        return bn_act(x, self.weight, self.bias, self.running_mean, self.running_var,
+                      residual=residual, relu=self.relu, training=self.training or not self.track_running_stats,
+                      momentum=0.1 if self.momentum is None else self.momentum, eps=self.eps, fused=self.fused)
+
+
+def _conv3x3(cin, cout, stride=1, groups=1, dilation=1):
+    return nn.Conv2d(cin, cout, 3, stride=stride, padding=dilation, groups=groups, bias=False, dilation=dilation)
+
+
+def _conv1x1(cin, cout, stride=1):
+    return nn.Conv2d(cin, cout, 1, stride=stride, bias=False)
+
+
+class _Downsample(nn.Sequential):
+    """conv1x1 + BN (no ReLU); indices 0/1 keep torchvision's ``downsample.0/1`` keys."""
+
+    def __init__(self, cin, cout, stride, fused):
+        super().__init__(_conv1x1(cin, cout, stride), BNAct(cout, relu=False, fused=fused))
+
+
+class BasicBlock(nn.Module):
+    expansion = 1
+
+    def __init__(self, cin, planes, stride=1, downsample=None, groups=1, base_width=64, fused=None):
+        super().__init__()
+        if groups != 1 or base_width != 64:
+            raise ValueError("BasicBlock only supports groups=1 and base_width=64")
+        self.conv1 = _conv3x3(cin, planes, stride)
+        self.bn1 = BNAct(planes, relu=True, fused=fused)
+        self.conv2 = _conv3x3(planes, planes)
+        self.bn2 = BNAct(planes, relu=True, fused=fused)
+        self.downsample = downsample
+        self.stride = stride
+
+    def forward(self, x):
+        identity = x if self.downsample is None else self.downsample(x)
+        out = self.bn1(self.conv1(x))
+        return self.bn2(self.conv2(out), identity)
+
+
+class Bottleneck(nn.Module):
+    expansion = 4
+
+    def __init__(self, cin, planes, stride=1, downsample=None, groups=1, base_width=64, fused=None):
+        super().__init__()
+        width = int(planes * (base_width / 64.0)) * groups
+        self.conv1 = _conv1x1(cin, width)
+        self.bn1 = BNAct(width, relu=True, fused=fused)
+        self.conv2 = _conv3x3(width, width, stride, groups)
+        self.bn2 = BNAct(width, relu=True, fused=fused)
+        self.conv3 = _conv1x1(width, planes * self.expansion)
+        self.bn3 = BNAct(planes * self.expansion, relu=True, fused=fused)
+        self.downsample = downsample
+        self.stride = stride
+
+    def forward(self, x):
+        identity = x if self.downsample is None else self.downsample(x)
+        out = self.bn1(self.conv1(x))
+        out = self.bn2(self.conv2(out))
+        return self.bn3(self.conv3(out), identity)
+
+
+class ResNet(nn.Module):
+    def __init__(self, block, layers, num_classes=1000, groups=1, width_per_group=64, fused_bn=None,
+                 zero_init_residual=False):
+        super().__init__()
+        self.inplanes = 64
+        self.groups = groups
+        self.base_width = width_per_group
+        self.fused_bn = fused_bn
+        self.conv1 = nn.Conv2d(3, 64, 7, stride=2, padding=3, bias=False)
+        self.bn1 = BNAct(64, relu=True, fused=fused_bn)
+        self.maxpool = nn.MaxPool2d(3, stride=2, padding=1)
+        self.layer1 = self._make_layer(block, 64, layers[0])
+        self.layer2 = self._make_layer(block, 128, layers[1], stride=2)
+        self.layer3 = self._make_layer(block, 256, layers[2], stride=2)
+        self.layer4 = self._make_layer(block, 512, layers[3], stride=2)
+        self.avgpool = nn.AdaptiveAvgPool2d((1, 1))
+        self.fc = nn.Linear(512 * block.expansion, num_classes)
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+            elif isinstance(m, nn.BatchNorm2d):
+                nn.init.constant_(m.weight, 1.0)
+                nn.init.constant_(m.bias, 0.0)
+        if zero_init_residual:
+            for m in self.modules():
+                if isinstance(m, Bottleneck):
+                    nn.init.constant_(m.bn3.weight, 0.0)
+                elif isinstance(m, BasicBlock):
+                    nn.init.constant_(m.bn2.weight, 0.0)
+
+    def _make_layer(self, block, planes, blocks, stride=1):
+        down = None
+        if stride != 1 or self.inplanes != planes * block.expansion:
+            down = _Downsample(self.inplanes, planes * block.expansion, stride, self.fused_bn)
+        layers = [block(self.inplanes, planes, stride, down, self.groups, self.base_width, self.fused_bn)]
+        self.inplanes = planes * block.expansion
+        for _ in range(1, blocks):
+            layers.append(block(self.inplanes, planes, groups=self.groups, base_width=self.base_width,
+                                fused=self.fused_bn))
+        return nn.Sequential(*layers)
+
+    def forward(self, x):
+        x = self.maxpool(self.bn1(self.conv1(x)))
+        x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
+        return self.fc(torch.flatten(self.avgpool(x), 1))
+
+
+def _factory(block, layers, **fixed):
+    def make(num_classes=1000, fused_bn=None, **kw):
+        return ResNet(block, layers, num_classes=num_classes, fused_bn=fused_bn, **fixed, **kw)
+    return make
+
+
+FACTORIES = {
+    "resnet18": _factory(BasicBlock, [2, 2, 2, 2]),
+    "resnet34": _factory(BasicBlock, [3, 4, 6, 3]),
+    "resnet50": _factory(Bottleneck, [3, 4, 6, 3]),
+    "resnet101": _factory(Bottleneck, [3, 4, 23, 3]),
+    "resnet152": _factory(Bottleneck, [3, 8, 36, 3]),
+    "resnext50_32x4d": _factory(Bottleneck, [3, 4, 6, 3], groups=32, width_per_group=4),
+    "resnext101_32x8d": _factory(Bottleneck, [3, 4, 23, 3], groups=32, width_per_group=8),
+    "resnext101_64x4d": _factory(Bottleneck, [3, 4, 23, 3], groups=64, width_per_group=4),
+    "wide_resnet50_2": _factory(Bottleneck, [3, 4, 6, 3], width_per_group=128),
+    "wide_resnet101_2": _factory(Bottleneck, [3, 4, 23, 3], width_per_group=128),
+}
