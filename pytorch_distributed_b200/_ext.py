@@ -116,3 +116,13 @@ def require_on_cuda() -> None:
     import torch
     if torch.cuda.is_available():
         lib()
+
+
+# ---------------------------------------------------------------------- launch accounting (bench.py "gpu_launches")
+launches = 0
+
+
+def note_launch(n: int = 1) -> None:
+    """Python wrappers of the native kernels call this once per kernel they enqueue."""
+    global launches
+    launches += n

@@ -1,0 +1,489 @@
+"""The shared training driver: ``main_worker`` / ``train`` / ``validate`` written ONCE for all entrypoints.
+
+The reference copies these ~250 lines into each of its six scripts (/root/reference/distributed.py:129-324 and the
+five siblings); the per-script differences are captured here by small :class:`Strategy` objects.
+
+Hot-loop differences from the reference (/root/reference/distributed.py:242-276), all behaviour-preserving:
+  * H2D copies run on a side stream with a fused normalise/cast/NHWC kernel (every entrypoint, not only apex);
+  * accuracy + ``barrier`` + 3x ``reduce_mean`` + 3x ``.item()`` collapse into ONE low-latency kernel whose result
+    is fetched asynchronously (the meters lag the GPU by at most ``--print-freq`` iterations and are drained before
+    every print), so the host never stalls the device inside the loop;
+  * gradient all-reduce, optimizer and loss scaling run through the fused sm_100a kernels.
+Output contract (progress lines, `` * Acc@1`` summary, checkpoint files) is the reference's.
+"""
+from __future__ import annotations
+
+import csv
+import json
+import os
+import random
+import time
+import warnings
+from collections import deque
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from . import cli
+from .models import create_model
+from .utils.checkpoint import export_state_dict, load_checkpoint, save_checkpoint
+from .utils.data import DataPrefetcher, build_loaders
+from .utils.meters import AverageMeter, ProgressMeter, accuracy, adjust_learning_rate
+
+_DTYPES = {"fp32": torch.float32, "bf16": torch.bfloat16, "fp16": torch.float16}
+
+
+def seed_everything(args) -> None:
+    """/root/reference/distributed.py:116-124"""
+    if args.seed is not None:
+        random.seed(args.seed)
+        torch.manual_seed(args.seed)
+        torch.backends.cudnn.deterministic = True
+        warnings.warn("You have chosen to seed training. This will turn on the CUDNN deterministic setting, "
+                      "which can slow down your training considerably! You may see unexpected behavior when "
+                      "restarting from checkpoints.")
+
+
+def pick_device(args, local_rank: int) -> torch.device:
+    want = args.device or ("cuda" if torch.cuda.is_available() else "cpu")
+    if want.startswith("cuda"):
+        torch.cuda.set_device(local_rank)
+        return torch.device("cuda", local_rank)
+    return torch.device("cpu")
+
+
+# ====================================================================== metrics
+class MetricPipeline:
+    """Asynchronous (loss, acc1, acc5) reduction: launch now, read later.
+
+    GPU: one K4 kernel (top-k counting + LL all-reduce over NVLink) + a 16-byte D2H copy into a pinned ring slot +
+    an event.  The meters are updated when the event has completed (``poll``) or on ``drain``.
+    CPU / library backends: computed eagerly with torch ops (gloo all-reduce).
+    """
+
+    def __init__(self, comm, device, meters, reduce: bool = True, depth: int = 64):
+        self.comm = comm
+        self.device = device
+        self.losses, self.top1, self.top5 = meters
+        self.reduce = reduce and comm is not None
+        self.cuda = device.type == "cuda"
+        self.pending = deque()
+        self.d2h_bytes = 0
+        self.last = (0.0, 0.0, 0.0)
+        if self.cuda:
+            self.ring = [torch.zeros(4, dtype=torch.float32).pin_memory() for _ in range(depth)]
+            self.dev = [torch.zeros(4, dtype=torch.float32, device=device) for _ in range(depth)]
+            self.slot = 0
+
+    def push(self, output, target, loss, n: int) -> None:
+        if not self.cuda:
+            out = torch.zeros(4)
+            if self.reduce:
+                self.comm.metrics(output.detach(), target, loss.detach(), out)
+            else:
+                a1, a5 = accuracy(output.detach(), target, topk=(1, 5))
+                out[0], out[1], out[2] = loss.detach().float(), a1[0], a5[0]
+            self._apply(out.tolist(), n)
+            return
+        if len(self.pending) >= len(self.ring) - 1:
+            self.poll(block_oldest=True)
+        i = self.slot
+        self.slot = (self.slot + 1) % len(self.ring)
+        dev = self.dev[i]
+        lossf = loss.detach()
+        if lossf.dtype != torch.float32:
+            lossf = lossf.float()
+        if self.reduce and getattr(self.comm, "backend", "") == "fused":
+            self.comm.metrics(output.detach(), target, lossf, dev)
+        else:
+            from . import _ext
+            C = _ext.lib()
+            _local_metrics(C, output.detach(), target, lossf, dev)
+            if self.reduce and self.comm.world > 1:
+                self.comm.reduce_scalars_(dev[:3], average=True)
+        self.ring[i].copy_(dev, non_blocking=True)
+        self.d2h_bytes += 16
+        ev = torch.cuda.Event()
+        ev.record()
+        self.pending.append((ev, i, n))
+
+    def _apply(self, vals, n):
+        self.last = (vals[0], vals[1], vals[2])
+        self.losses.update(vals[0], n)
+        self.top1.update(vals[1], n)
+        self.top5.update(vals[2], n)
+
+    def poll(self, block_oldest: bool = False) -> None:
+        while self.pending:
+            ev, i, n = self.pending[0]
+            if block_oldest:
+                ev.synchronize()
+                block_oldest = False
+            elif not ev.query():
+                break
+            self.pending.popleft()
+            self._apply(self.ring[i].tolist(), n)
+
+    def drain(self) -> None:
+        while self.pending:
+            self.poll(block_oldest=True)
+
+
+_single_arena = {}
+
+
+def _local_metrics(C, output, target, loss, out):
+    """K4 without peers (world == 1 arena): used by DataParallel / library-comm runs on a GPU."""
+    dev = output.device.index
+    a = _single_arena.get(dev)
+    if a is None:
+        a = C.SymmArena(dev, 0, 1, 1 << 21)
+        _single_arena[dev] = a
+    from . import _ext
+    _ext.note_launch()
+    a.launch_metrics(0, output, target, loss, out)
+
+
+# ====================================================================== strategies
+class Strategy:
+    """What differs between the reference scripts."""
+
+    name = "distributed"
+    distributed = True          # one process per GPU with a process group
+    shard_batch = True          # per-process batch = -b / world
+    reduce_metrics = True
+    raw_uint8_loader = False
+    cast_params = True          # low precision = cast the model (fp32 masters in FusedSGD); False => autocast
+    epoch_csv: Optional[str] = None
+
+    def init_process_group(self, args, local_rank: int, nprocs: int) -> None:
+        backend = args.dist_backend or ("nccl" if (args.device or "cuda").startswith("cuda") and torch.cuda.is_available() else "gloo")
+        kw = {}
+        if backend == "nccl":
+            kw["device_id"] = torch.device("cuda", local_rank)
+        if args.dist_url:
+            dist.init_process_group(backend=backend, init_method=args.dist_url, world_size=nprocs, rank=local_rank, **kw)
+        else:
+            dist.init_process_group(backend=backend, **kw)
+
+    def world(self):
+        return dist.get_world_size() if dist.is_initialized() else 1
+
+    def rank(self):
+        return dist.get_rank() if dist.is_initialized() else 0
+
+    def is_saver(self, args) -> bool:
+        return self.rank() == 0
+
+    def comm_kind(self, args, device) -> str:
+        if args.comm != "auto":
+            return args.comm
+        return "fused" if device.type == "cuda" else "gloo"
+
+    def prepare_model(self, model, args, device):
+        """Precision / layout policy for the plain-DDP style entrypoints."""
+        model.to(device)
+        prec = args.precision or ("bf16" if device.type == "cuda" else "fp32")
+        args.precision = prec
+        cl = args.channels_last if args.channels_last is not None else device.type == "cuda"
+        args.channels_last = cl
+        if cl:
+            model.to(memory_format=torch.channels_last)
+        self.autocast = None
+        if prec != "fp32":
+            if args.optimizer == "fused" and device.type == "cuda" and self.cast_params:
+                from .parallel.amp import cast_model
+                cast_model(model, _DTYPES[prec], keep_batchnorm_fp32=True)   # fp32 masters live in FusedSGD
+            else:
+                self.autocast = _DTYPES[prec]                                # stock optimizer: fp32 weights + autocast
+        self.input_dtype = _DTYPES[prec] if (prec != "fp32" and self.autocast is None) else torch.float32
+        return model
+
+    def make_optimizer(self, model, args):
+        if args.optimizer == "fused":
+            from .ops.fused_sgd import FusedSGD
+            return FusedSGD(model.parameters(), args.lr, momentum=args.momentum, weight_decay=args.weight_decay)
+        return torch.optim.SGD(model.parameters(), args.lr, momentum=args.momentum, weight_decay=args.weight_decay)
+
+    def wrap(self, model, args, device, local_rank):
+        from .parallel.ddp import DistributedDataParallel
+        wire = args.wire_dtype if device.type == "cuda" else "fp32"
+        model = DistributedDataParallel(model, device_ids=[local_rank] if device.type == "cuda" else None,
+                                        comm=self.comm_kind(args, device), wire_dtype=wire, bucket_cap_mb=args.bucket_cap_mb)
+        self.comm = model.comm
+        self.engine = model.engine
+        return model
+
+    def build(self, model, args, device, local_rank):
+        model = self.prepare_model(model, args, device)
+        model = self.wrap(model, args, device, local_rank)
+        optimizer = self.make_optimizer(model, args)
+        return model, optimizer
+
+    def forward(self, model, images):
+        if self.autocast is not None:
+            with torch.autocast(device_type=images.device.type, dtype=self.autocast):
+                return model(images)
+        return model(images)
+
+    def backward(self, loss, optimizer):
+        loss.backward()
+
+    def unwrapped(self, model):
+        return model.module if hasattr(model, "module") else model
+
+    def prefetcher(self, loader, device, args, limit=None):
+        return DataPrefetcher(loader, device, dtype=self.input_dtype, channels_last=bool(args.channels_last),
+                              normalize="imagenet255" if self.raw_uint8_loader else None, limit=limit)
+
+
+class ApexStrategy(Strategy):
+    """/root/reference/apex_distributed.py: amp.initialize + apex DDP + scale_loss + data_prefetcher."""
+    name = "apex_distributed"
+    raw_uint8_loader = False
+
+    def build(self, model, args, device, local_rank):
+        from .apex import amp
+        from .apex.parallel import DistributedDataParallel as ApexDDP
+        model.to(device)
+        cl = args.channels_last if args.channels_last is not None else device.type == "cuda"
+        args.channels_last = cl
+        if cl:
+            model.to(memory_format=torch.channels_last)
+        prec = args.precision or ("fp16" if device.type == "cuda" else "bf16")
+        args.precision = prec
+        half = _DTYPES[prec] if prec != "fp32" else torch.float16
+        opt_level = "O0" if prec == "fp32" else args.opt_level
+        optimizer = self.make_optimizer(model, args)
+        ls = args.loss_scale if args.loss_scale == "dynamic" else float(args.loss_scale)
+        model, optimizer = amp.initialize(model, optimizer, opt_level=opt_level, loss_scale=ls if opt_level != "O0" else 1.0,
+                                          half_dtype=half, verbosity=0 if args.quiet else 1)
+        self.amp = amp
+        wire = "fp32" if device.type != "cuda" or opt_level == "O0" else ("fp16" if half == torch.float16 else "bf16")
+        if args.wire_dtype != "bf16":   # explicit override
+            wire = args.wire_dtype
+        model = ApexDDP(model, comm=self.comm_kind(args, device), wire_dtype=wire)
+        self.comm = model.comm
+        self.engine = model.engine
+        self.autocast = None            # amp wrapped the forward already
+        self.input_dtype = half if opt_level in ("O2", "O3") else torch.float32
+        return model, optimizer
+
+    def backward(self, loss, optimizer):
+        with self.amp.scale_loss(loss, optimizer) as scaled_loss:
+            scaled_loss.backward()
+
+
+class HorovodStrategy(Strategy):
+    """/root/reference/horovod_distributed.py: broadcast_parameters + DistributedOptimizer(compression=fp16)."""
+    name = "horovod_distributed"
+    cast_params = False         # gradients come back decompressed to fp32 into p.grad: keep fp32 weights + autocast
+
+    def init_process_group(self, args, local_rank, nprocs):
+        from .parallel import hvd
+        hvd.init(comm=args.comm if args.comm != "auto" else None, device=args.device)
+        self.hvd = hvd
+
+    def world(self):
+        return self.hvd.size()
+
+    def rank(self):
+        return self.hvd.rank()
+
+    def build(self, model, args, device, local_rank):
+        hvd = self.hvd
+        model = self.prepare_model(model, args, device)
+        hvd.broadcast_parameters(model.state_dict(), root_rank=0)
+        optimizer = self.make_optimizer(model, args)
+        hvd.broadcast_optimizer_state(optimizer, root_rank=0)
+        comp = {"none": hvd.Compression.none, "fp16": hvd.Compression.fp16, "bf16": hvd.Compression.bf16}[args.compression]
+        if device.type != "cuda":
+            comp = hvd.Compression.none
+        optimizer = hvd.DistributedOptimizer(optimizer, named_parameters=model.named_parameters(), compression=comp)
+        self.comm = hvd.communicator()
+        self.engine = getattr(optimizer, "_ptd_engine_obj", None)
+        return model, optimizer
+
+
+class DataParallelStrategy(Strategy):
+    """/root/reference/dataparallel.py: one process drives every GPU."""
+    name = "dataparallel"
+    distributed = False
+    shard_batch = False
+    reduce_metrics = False
+    epoch_csv = "dataparallel.csv"
+
+    def init_process_group(self, args, local_rank, nprocs):
+        pass
+
+    def build(self, model, args, device, local_rank):
+        from .parallel.dp import DataParallel
+        if args.gpus:
+            gpus = [int(g) for g in args.gpus.split(",")]
+        else:
+            gpus = list(range(torch.cuda.device_count())) if device.type == "cuda" else []
+        model = self.prepare_model(model, args, device)
+        model = DataParallel(model, device_ids=gpus, output_device=gpus[0] if gpus else None,
+                             compute_dtype=self.input_dtype if self.autocast is None else None)
+        self.comm = None
+        self.engine = model.engine
+        optimizer = self.make_optimizer(model, args)
+        return model, optimizer
+
+
+class SlurmStrategy(Strategy):
+    """/root/reference/distributed_slurm_main.py (global-rank-0 checkpoint guard instead of every rank, Q11)."""
+    name = "distributed_slurm_main"
+    epoch_csv = "distributed.csv"
+
+
+STRATEGIES = {
+    "distributed": Strategy,
+    "multiprocessing_distributed": Strategy,
+    "apex_distributed": ApexStrategy,
+    "horovod_distributed": HorovodStrategy,
+    "dataparallel": DataParallelStrategy,
+    "distributed_slurm_main": SlurmStrategy,
+}
+
+
+# ====================================================================== the worker
+def main_worker(local_rank: int, nprocs: int, args, strategy: Optional[Strategy] = None):
+    """/root/reference/distributed.py:129-225 (shared by every entrypoint)."""
+    st = strategy or STRATEGIES[args.entry]()
+    best_acc1 = 0.0
+    device = pick_device(args, local_rank)
+    args.local_rank = local_rank
+    st.init_process_group(args, local_rank, nprocs)
+    world = st.world() if st.distributed else 1
+
+    model = create_model(args.arch, pretrained=args.pretrained, num_classes=args.num_classes, fused_bn=args.fused_bn)
+    # per-process batch: "-b" is the total over the node (reference :146); DataParallel keeps the full batch (:166)
+    args.total_batch_size = args.batch_size
+    if st.shard_batch:
+        args.batch_size = max(1, int(args.batch_size / world))
+    model, optimizer = st.build(model, args, device, local_rank)
+    criterion = nn.CrossEntropyLoss().to(device)
+    torch.backends.cudnn.benchmark = True
+
+    train_loader, val_loader, train_sampler, val_sampler = build_loaders(args, args.batch_size, distributed=st.distributed,
+                                                                        raw_uint8=st.raw_uint8_loader)
+    if args.resume:
+        ck = load_checkpoint(args.resume, st.unwrapped(model), optimizer)
+        args.start_epoch = ck.get("epoch", args.start_epoch)
+        best_acc1 = float(ck.get("best_acc1", 0.0))
+        print("=> loaded checkpoint '{}' (epoch {})".format(args.resume, args.start_epoch))
+
+    if args.evaluate:
+        validate(val_loader, model, criterion, st, device, args)
+        _shutdown(st)
+        return
+
+    for epoch in range(args.start_epoch, args.epochs):
+        t_epoch = time.time()
+        train_sampler.set_epoch(epoch)
+        val_sampler.set_epoch(epoch)
+        adjust_learning_rate(optimizer, epoch, args)
+        train(train_loader, model, criterion, optimizer, epoch, st, device, args)
+        acc1 = validate(val_loader, model, criterion, st, device, args)
+        is_best = acc1 > best_acc1
+        best_acc1 = max(acc1, best_acc1)
+        if st.epoch_csv and st.is_saver(args):
+            with open(os.path.join(args.checkpoint_dir, st.epoch_csv), "a+", newline="") as f:
+                csv.writer(f).writerow([time.strftime("%Y-%m-%d %H:%M:%S", time.localtime(t_epoch)), time.time() - t_epoch])
+        if st.is_saver(args):
+            save_checkpoint({
+                "epoch": epoch + 1,
+                "arch": args.arch,
+                "state_dict": export_state_dict(st.unwrapped(model), getattr(st, "engine", None)),
+                "best_acc1": best_acc1,
+                "optimizer": optimizer.state_dict() if args.resume or os.environ.get("PTD_SAVE_OPTIMIZER") else None,
+            }, is_best, directory=args.checkpoint_dir)
+    _shutdown(st)
+
+
+def _shutdown(st):
+    comm = getattr(st, "comm", None)
+    if comm is not None:
+        comm.check()
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    if st.distributed and dist.is_initialized():
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def _log_jsonl(args, rec):
+    if args.log_jsonl:
+        with open(args.log_jsonl, "a") as f:
+            f.write(json.dumps(rec) + "\n")
+
+
+def train(train_loader, model, criterion, optimizer, epoch, st: Strategy, device, args):
+    """/root/reference/distributed.py:228-276"""
+    batch_time = AverageMeter("Time", ":6.3f")
+    data_time = AverageMeter("Data", ":6.3f")
+    losses = AverageMeter("Loss", ":.4e")
+    top1 = AverageMeter("Acc@1", ":6.2f")
+    top5 = AverageMeter("Acc@5", ":6.2f")
+    pf = st.prefetcher(train_loader, device, args, limit=args.steps_per_epoch)
+    progress = ProgressMeter(len(pf), [batch_time, data_time, losses, top1, top5], prefix="Epoch: [{}]".format(epoch))
+    metrics = MetricPipeline(getattr(st, "comm", None), device, (losses, top1, top5), reduce=st.reduce_metrics)
+    model.train()
+    end = time.time()
+    t0 = end
+    n_img = 0
+    for i, (images, target) in enumerate(pf):
+        data_time.update(time.time() - end)
+        output = st.forward(model, images)
+        loss = criterion(output.float() if output.dtype != torch.float32 else output, target)
+        metrics.push(output, target, loss, images.size(0))
+        optimizer.zero_grad()
+        st.backward(loss, optimizer)
+        optimizer.step()
+        n_img += images.size(0)
+        metrics.poll()
+        batch_time.update(time.time() - end)
+        end = time.time()
+        if i % args.print_freq == 0:
+            metrics.drain()
+            if not args.quiet:
+                progress.display(i)
+    metrics.drain()
+    if device.type == "cuda":
+        torch.cuda.synchronize(device)
+    _log_jsonl(args, {"phase": "train", "epoch": epoch, "rank": st.rank() if st.distributed else 0, "images": n_img,
+                      "seconds": time.time() - t0, "loss": losses.avg, "acc1": top1.avg, "acc5": top5.avg})
+    return losses.avg
+
+
+def validate(val_loader, model, criterion, st: Strategy, device, args):
+    """/root/reference/distributed.py:279-324 - distributed evaluation: sharded val set + metric all-reduce."""
+    batch_time = AverageMeter("Time", ":6.3f")
+    losses = AverageMeter("Loss", ":.4e")
+    top1 = AverageMeter("Acc@1", ":6.2f")
+    top5 = AverageMeter("Acc@5", ":6.2f")
+    pf = st.prefetcher(val_loader, device, args, limit=args.val_steps or args.steps_per_epoch)
+    progress = ProgressMeter(len(pf), [batch_time, losses, top1, top5], prefix="Test: ")
+    metrics = MetricPipeline(getattr(st, "comm", None), device, (losses, top1, top5), reduce=st.reduce_metrics)
+    model.eval()
+    with torch.no_grad():
+        end = time.time()
+        for i, (images, target) in enumerate(pf):
+            output = st.forward(model, images)
+            loss = criterion(output.float() if output.dtype != torch.float32 else output, target)
+            metrics.push(output, target, loss, images.size(0))
+            metrics.poll()
+            batch_time.update(time.time() - end)
+            end = time.time()
+            if i % args.print_freq == 0:
+                metrics.drain()
+                if not args.quiet:
+                    progress.display(i)
+        metrics.drain()
+        # TODO(reference parity): this line is printed by every rank, like the reference
+        print(" * Acc@1 {top1.avg:.3f} Acc@5 {top5.avg:.3f}".format(top1=top1, top5=top5), flush=True)
+    _log_jsonl(args, {"phase": "val", "rank": st.rank() if st.distributed else 0, "loss": losses.avg, "acc1": top1.avg, "acc5": top5.avg})
+    return top1.avg

@@ -14,7 +14,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from ..ops.bn_act import bn_act
+from ..ops.bn_act import begin_step, bn_act
 
 
 class BNAct(nn.BatchNorm2d):
@@ -132,6 +132,8 @@ class ResNet(nn.Module):
         return nn.Sequential(*layers)
 
     def forward(self, x):
+        if self.training:
+            begin_step(x.device)      # recycle the BN accumulator workspace: one memset per step
         x = self.maxpool(self.bn1(self.conv1(x)))
         x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
         return self.fc(torch.flatten(self.avgpool(x), 1))

@@ -1,0 +1,1 @@
+"""Hand-written sm_100a ops with PyTorch reference fall-backs (CPU / oracle)."""

@@ -1,0 +1,160 @@
+"""FusedSGD: SGD with momentum / weight decay as hand-written sm_100a kernels (``csrc/optim.cu``).
+
+Drop-in for ``torch.optim.SGD`` as used at /root/reference/distributed.py:153-156 and, together with
+:mod:`..parallel.amp`, for apex's patched optimizer + ``amp_C`` kernels (/root/reference/apex_distributed.py:211-216,330).
+
+Three execution modes, picked automatically:
+  * **flat / arena** - the parameters belong to one of our data-parallel engines: the reduced gradients are read
+    directly from the symmetric wire arena (no write-back into ``p.grad``), master weights / momentum / model copy are
+    flat buffers with the arena's layout, and the whole step is ONE streaming kernel.
+  * **multi-tensor** - CUDA parameters without an engine: chunked multi-tensor-apply kernel over ``p.grad``.
+  * **reference** - CPU tensors: plain PyTorch math (also the numerical oracle for the tests).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+from torch.optim import Optimizer
+
+
+def sgd_reference_step(p, g, buf, lr, momentum, weight_decay, dampening, nesterov, first):
+    """torch.optim.SGD semantics on plain tensors (fp32 math)."""
+    g = g.float()
+    if weight_decay != 0:
+        g = g.add(p.float(), alpha=weight_decay)
+    if momentum != 0:
+        if first:
+            buf.copy_(g)
+        else:
+            buf.mul_(momentum).add_(g, alpha=1 - dampening)
+        g = g.add(buf, alpha=momentum) if nesterov else buf
+    p.add_(g.to(p.dtype), alpha=-lr)
+
+
+class FusedSGD(Optimizer):
+    def __init__(self, params, lr=0.1, momentum=0.0, dampening=0.0, weight_decay=0.0, nesterov=False, flat: Optional[bool] = None):
+        if nesterov and (momentum <= 0 or dampening != 0):
+            raise ValueError("Nesterov momentum requires a momentum and zero dampening")
+        defaults = dict(lr=lr, momentum=momentum, dampening=dampening, weight_decay=weight_decay, nesterov=nesterov)
+        super().__init__(params, defaults)
+        self._steps = 0
+        self._flat = None           # _FlatState when bound to an engine
+        self._hyper = {}            # group index -> (device tensor, cached python tuple)
+        self._amp = None            # LossScaler (set by amp.initialize)
+        self._want_flat = flat
+        self._try_bind()
+
+    # ------------------------------------------------------------------ engine binding (flat mode)
+    def _try_bind(self):
+        if self._want_flat is False or len(self.param_groups) != 1:
+            return
+        params = [p for p in self.param_groups[0]["params"] if p.requires_grad]
+        if not params or not all(p.is_cuda for p in params):
+            return
+        engines = {getattr(p, "_ptd_engine", None) for p in params}
+        if len(engines) != 1:
+            return
+        ref = engines.pop()
+        eng = ref() if ref is not None else None
+        if eng is None or not getattr(eng, "supports_flat_optimizer", False):
+            return
+        self._flat = eng.bind_flat_optimizer(self, params)
+
+    @property
+    def is_flat(self) -> bool:
+        return self._flat is not None
+
+    # ------------------------------------------------------------------ hyper-parameters on the device
+    def _hyper_tensor(self, gi: int, group, device):
+        gmul = 1.0
+        vals = (float(group["lr"]), float(group["momentum"]), float(group["weight_decay"]), float(group["dampening"]))
+        ent = self._hyper.get(gi)
+        if ent is None:
+            t = torch.tensor(list(vals) + [gmul, 0, 0, 0], dtype=torch.float32, device=device)
+            self._hyper[gi] = [t, vals]
+            return t
+        if ent[1] != vals:
+            # only lr..dampening are host-owned; slot 4 (gradient multiplier) belongs to the loss scaler kernel
+            ent[0][:4].copy_(torch.tensor(vals, dtype=torch.float32), non_blocking=True)
+            ent[1] = vals
+        return ent[0]
+
+    # ------------------------------------------------------------------ step
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        first = self._steps == 0
+        amp = self._amp
+        if self._flat is None and first:
+            self._try_bind()      # the engine may have been created after this optimizer (apex order: amp -> DDP)
+        if self._flat is not None:
+            fs = self._flat
+            fs.engine.wait_for_gradients()
+            group = self.param_groups[0]
+            hyper = self._hyper_tensor(0, group, fs.master.device)
+            if amp is not None:
+                amp.attach_hyper(hyper)
+            from .. import _ext
+            _ext.note_launch()
+            _ext.lib().fused_sgd_flat(fs.engine.grad_arena(), fs.master, fs.momentum, fs.model_copy, hyper,
+                                      amp.found_inf if amp is not None else None, bool(group["nesterov"]), first)
+            if amp is not None:
+                amp.update()
+        else:
+            for gi, group in enumerate(self.param_groups):
+                self._step_group(gi, group, first, amp)
+            if amp is not None:
+                amp.update()
+        self._steps += 1
+        return loss
+
+    def _step_group(self, gi, group, first, amp):
+        params = [p for p in group["params"] if p.grad is not None]
+        if not params:
+            return
+        bufs = []
+        for p in params:
+            st = self.state[p]
+            if "momentum_buffer" not in st:
+                st["momentum_buffer"] = torch.zeros_like(p, dtype=torch.float32, memory_format=torch.preserve_format)
+                st["_fresh"] = True
+            bufs.append(st["momentum_buffer"])
+        if params[0].is_cuda and all(p.dtype == torch.float32 for p in params):
+            from .. import _ext
+            C = _ext.lib()
+            hyper = self._hyper_tensor(gi, group, params[0].device)
+            if amp is not None:
+                amp.attach_hyper(hyper)
+            fresh = [p for p in params if self.state[p].pop("_fresh", False)]
+            if fresh and len(fresh) != len(params):
+                # rare: parameters that got their first gradient later than the others
+                for sub, f in ((fresh, True), ([p for p in params if p not in set(fresh)], False)):
+                    C.fused_sgd_multi([p.grad for p in sub], list(sub), [self.state[p]["momentum_buffer"] for p in sub], [], hyper,
+                                      amp.found_inf if amp is not None else None, bool(group["nesterov"]), f)
+            else:
+                C.fused_sgd_multi([p.grad for p in params], params, bufs, [], hyper,
+                                  amp.found_inf if amp is not None else None, bool(group["nesterov"]), bool(fresh))
+        else:
+            if amp is not None and amp.host_found_inf():
+                return
+            gmul = amp.host_inv_scale() if amp is not None else 1.0
+            for p, buf in zip(params, bufs):
+                fresh = self.state[p].pop("_fresh", False)
+                g = p.grad if gmul == 1.0 else p.grad.float() * gmul
+                if p.dtype == torch.float32:
+                    sgd_reference_step(p, g, buf, group["lr"], group["momentum"], group["weight_decay"], group["dampening"],
+                                       group["nesterov"], fresh)
+                else:
+                    st = self.state[p]
+                    if "master" not in st:
+                        st["master"] = p.detach().float().clone()
+                    sgd_reference_step(st["master"], g, buf, group["lr"], group["momentum"], group["weight_decay"],
+                                       group["dampening"], group["nesterov"], fresh)
+                    p.copy_(st["master"])
+
+    def zero_grad(self, set_to_none: bool = True):
+        super().zero_grad(set_to_none=set_to_none)

@@ -1,0 +1,315 @@
+"""DistributedDataParallel: one process per GPU, gradient buckets reduced during backward by the fused
+peer-memory kernel (K1) instead of torch's C++ Reducer + NCCL.
+
+API parity with the reference's use (/root/reference/distributed.py:147-148,223):
+``DistributedDataParallel(model, device_ids=[local_rank])``, ``.module``, ``model(images)``, hooks fire inside
+``loss.backward()``.  Behaviour parity with torch's Reducer defaults: rank-0 parameters/buffers are broadcast at
+construction, float buffers are re-broadcast from rank 0 before every forward (``broadcast_buffers=True``), buckets
+are 1 MiB (first) / ``bucket_cap_mb`` in reverse registration order, gradients are averaged.
+
+B200-native design:
+  * the wire format is a symmetric arena mapped into every peer (``parallel/comm.py``); bucket ``k`` owns a fixed
+    range of it, so there is no flatten/copy-in: K1 reads the autograd-produced gradients through a pointer pack,
+    casts (fp32 -> bf16), pre-scales by 1/world and reduces in ONE kernel per bucket on a high-priority side stream;
+  * with :class:`~pytorch_distributed_b200.ops.fused_sgd.FusedSGD` the reduced arena is consumed in place by the
+    optimizer kernel (no write-back pass into ``p.grad``);
+  * small CTA counts (<= 32) + NVLS in-switch reduction keep the SMs for cuDNN while the bucket is in flight.
+"""
+from __future__ import annotations
+
+import weakref
+from contextlib import contextmanager
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from . import plan as P
+from ..utils.tensors import is_dense
+from .comm import KIND_TWO_SHOT, FusedCommunicator, TorchCommunicator, make_communicator
+
+_WIRE_OF = {torch.float32: "fp32", torch.bfloat16: "bf16", torch.float16: "fp16"}
+
+
+class _FlatState:
+    """Flat optimizer-side buffers that share the gradient arena's layout."""
+
+    def __init__(self, engine, master, momentum, model_copy):
+        self.engine = engine
+        self.master = master
+        self.momentum = momentum
+        self.model_copy = model_copy
+
+
+class _Bucket:
+    __slots__ = ("index", "param_ids", "plan", "pending", "launched", "elem_off")
+
+    def __init__(self, index, param_ids):
+        self.index = index
+        self.param_ids = param_ids
+        self.plan = None
+        self.pending = len(param_ids)
+        self.launched = False
+        self.elem_off = 0
+
+
+class GradientEngine:
+    """Bucketed, overlapped gradient all-reduce over a list of parameters (shared by DDP / apex DDP)."""
+
+    supports_flat_optimizer = True
+
+    def __init__(self, params: List[torch.nn.Parameter], comm, wire_dtype: str = "bf16", bucket_cap_mb: float = 25.0,
+                 first_bucket_mb: float = 1.0, max_ctas: Optional[int] = None, check_inf: bool = False, average: bool = True,
+                 order: str = "reverse"):
+        self.comm = comm
+        self.world = comm.world
+        self.fused = isinstance(comm, FusedCommunicator)
+        self.params = [p for p in params if p.requires_grad]
+        self.wire = wire_dtype
+        self.check_inf = check_inf
+        self.average = average
+        self.writeback = True           # flipped off when a flat FusedSGD consumes the arena directly
+        self.enabled = True             # no_sync()
+        self._flat: Optional[_FlatState] = None
+        self._callback_queued = False
+        self._pending_finish = []       # TorchCommunicator async handles
+        self._grads_ready_event = None
+        self._next_bucket = 0
+        esz = P.WIRE_BYTES[wire_dtype]
+        ids = list(range(len(self.params)))
+        if order == "reverse":
+            ids = ids[::-1]             # gradients become ready roughly in reverse registration order
+        numels = [self.params[i].numel() for i in ids]
+        max_t = 256
+        groups = P.compute_buckets(numels, esz, int(bucket_cap_mb * (1 << 20)), int(first_bucket_mb * (1 << 20)), max_t)
+        self.buckets = [_Bucket(k, [ids[j] for j in g]) for k, g in enumerate(groups)]
+        self.bucket_of = {}
+        for b in self.buckets:
+            for pid in b.param_ids:
+                self.bucket_of[pid] = b
+        self.param_elem_off = [0] * len(self.params)
+        if self.fused:
+            self.stream = torch.cuda.Stream(device=comm.device, priority=-1)
+            self.channel = comm.new_channel()
+            # one contiguous arena range for all buckets => the optimizer can treat it as a single flat tensor
+            layouts = []
+            for b in self.buckets:
+                ns = [self.params[i].numel() for i in b.param_ids]
+                offs, total = P.tensor_layout(ns)
+                grid = P.choose_grid(total, esz, min(max_ctas or comm.max_ctas, comm.max_blocks))
+                layouts.append((ns, offs, total, P.build_layout(ns, self.world, grid, offs, total).region_elems))
+            self.total_elems = sum(l[3] for l in layouts)
+            self.arena_off = comm.alloc(self.total_elems * esz)
+            cur = 0
+            for b, (ns, offs, total, region) in zip(self.buckets, layouts):
+                b.elem_off = cur
+                b.plan = comm.make_plan(ns, wire_dtype, max_ctas=max_ctas, double_buffer=False, offsets=offs, total=total,
+                                        data_off_bytes=self.arena_off + cur * esz)
+                assert b.plan.layout.region_elems == region
+                for pid, o in zip(b.param_ids, offs):
+                    self.param_elem_off[pid] = cur + o
+                cur += region
+            from .comm import _VIEW_NAME
+            self._arena_flat = comm.arena.view(self.arena_off, self.total_elems, _VIEW_NAME[wire_dtype], 0)
+        else:
+            self.stream = None
+            self.total_elems = 0
+        ref = weakref.ref(self)
+        self._hooks = []
+        for pid, p in enumerate(self.params):
+            p._ptd_engine = ref
+            p._ptd_index = pid
+            self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(pid)))
+
+    # ------------------------------------------------------------------ flat optimizer binding
+    def grad_arena(self) -> torch.Tensor:
+        return self._arena_flat
+
+    def bind_flat_optimizer(self, optimizer, params) -> Optional[_FlatState]:
+        if not self.fused or self._flat is not None:
+            return None
+        if [id(p) for p in params] != [id(p) for p in self.params]:
+            return None
+        dtypes = {p.dtype for p in self.params}
+        if len(dtypes) != 1:
+            return None
+        dt = dtypes.pop()
+        dev = self.comm.device
+        n = self.total_elems
+        master = torch.zeros(n, dtype=torch.float32, device=dev)
+        momentum = torch.zeros(n, dtype=torch.float32, device=dev)
+        model_copy = None if dt == torch.float32 else torch.zeros(n, dtype=dt, device=dev)
+        holder = master if model_copy is None else model_copy
+        with torch.no_grad():
+            for pid, p in enumerate(self.params):
+                off, cnt = self.param_elem_off[pid], p.numel()
+                if not is_dense(p):
+                    return None
+                view = holder[off:off + cnt].as_strided(p.size(), p.stride())
+                view.copy_(p.data)
+                if model_copy is not None:
+                    init = getattr(p, "_ptd_master_init", None)     # fp32 values stashed by amp.cast_model
+                    master[off:off + cnt].as_strided(p.size(), p.stride()).copy_(p.data.float() if init is None else init)
+                    if init is not None:
+                        del p._ptd_master_init
+                p.data = view
+                optimizer.state[p]["momentum_buffer"] = momentum[off:off + cnt].as_strided(p.size(), p.stride())
+        self._flat = _FlatState(self, master, momentum, model_copy)
+        self.writeback = False
+        return self._flat
+
+    def master_params(self):
+        """fp32 views of the master weights (== the parameters themselves unless a low-precision copy is in use)."""
+        if self._flat is None or self._flat.model_copy is None:
+            return [p.data for p in self.params]
+        return [self._flat.master[self.param_elem_off[i]:self.param_elem_off[i] + p.numel()].as_strided(p.size(), p.stride())
+                for i, p in enumerate(self.params)]
+
+    # ------------------------------------------------------------------ backward-time machinery
+    def _make_hook(self, pid):
+        def hook(param):
+            if not self.enabled:
+                return
+            if not self._callback_queued:
+                torch.autograd.Variable._execution_engine.queue_callback(self._finalize)
+                self._callback_queued = True
+            b = self.bucket_of[pid]
+            b.pending -= 1
+            if b.pending == 0:
+                self._launch_ready()
+        return hook
+
+    def _launch_ready(self):
+        while self._next_bucket < len(self.buckets) and self.buckets[self._next_bucket].pending == 0:
+            self._launch(self.buckets[self._next_bucket])
+            self._next_bucket += 1
+
+    def _bucket_grads(self, b):
+        grads = []
+        for pid in b.param_ids:
+            p = self.params[pid]
+            if p.grad is None:      # parameter unused in this iteration: contributes zeros
+                p.grad = torch.zeros_like(p, memory_format=torch.preserve_format)
+            g = p.grad
+            if not is_dense(g):
+                g = g.contiguous()
+                p.grad = g
+            grads.append(g)
+        return grads
+
+    def _launch(self, b):
+        grads = self._bucket_grads(b)
+        scale = (1.0 / self.world) if self.average else 1.0
+        if self.fused:
+            ev = torch.cuda.Event()
+            ev.record()
+            self.stream.wait_event(ev)
+            with torch.cuda.stream(self.stream):
+                self.comm.run(b.plan, grads, KIND_TWO_SHOT, self.channel, scale=scale, writeback=self.writeback,
+                              check_inf=self.check_inf)
+        else:
+            fin = self.comm.all_reduce_(grads, average=self.average, wire=self.wire, async_op=True)
+            if fin is not None:
+                self._pending_finish.append(fin)
+        b.launched = True
+
+    def _finalize(self):
+        """End of backward: flush stragglers, then make the compute stream wait for the comm stream."""
+        self._callback_queued = False
+        if self._next_bucket < len(self.buckets):
+            for b in self.buckets[self._next_bucket:]:
+                b.pending = 0
+            self._launch_ready()
+        if self.fused:
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+            self._grads_ready_event = ev
+            torch.cuda.current_stream().wait_event(ev)
+        else:
+            for fin in self._pending_finish:
+                fin()
+            self._pending_finish.clear()
+        for b in self.buckets:
+            b.pending = len(b.param_ids)
+            b.launched = False
+        self._next_bucket = 0
+
+    def wait_for_gradients(self):
+        if self._grads_ready_event is not None:
+            torch.cuda.current_stream().wait_event(self._grads_ready_event)
+
+    def reduce_now(self):
+        """Synchronously reduce whatever is in ``p.grad`` (used after ``no_sync`` accumulation or by tests)."""
+        for b in self.buckets:
+            b.pending = 0
+        self._next_bucket = 0
+        self._finalize()
+
+    def remove_hooks(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+
+
+def _float_buffers(module):
+    return [b for b in module.buffers() if b.is_floating_point()]
+
+
+def sync_module_states(module: nn.Module, comm, root: int = 0) -> None:
+    """Make every rank start from rank ``root``'s parameters and buffers (torch DDP ctor semantics)."""
+    if comm.world == 1:
+        return
+    with torch.no_grad():
+        tensors = [p.data for p in module.parameters()] + _float_buffers(module)
+        comm.broadcast_(tensors, root=root)
+        ints = [b for b in module.buffers() if not b.is_floating_point()]
+        if ints and dist.is_initialized():
+            for b in ints:
+                dist.broadcast(b, src=root, group=comm.group)
+
+
+class DistributedDataParallel(nn.Module):
+    def __init__(self, module: nn.Module, device_ids=None, output_device=None, dim=0, broadcast_buffers: bool = True,
+                 process_group=None, bucket_cap_mb: float = 25.0, find_unused_parameters: bool = False,
+                 gradient_as_bucket_view: bool = False, comm="auto", wire_dtype: Optional[str] = None, max_ctas: Optional[int] = None,
+                 check_inf: bool = False):
+        super().__init__()
+        self.module = module
+        params = [p for p in module.parameters() if p.requires_grad]
+        if not params:
+            raise RuntimeError("DistributedDataParallel is not needed when a module doesn't have any parameter that requires a gradient.")
+        self.device = params[0].device
+        if device_ids is not None and self.device.type == "cuda":
+            d = device_ids[0]
+            d = d.index if isinstance(d, torch.device) else int(d)
+            if d != self.device.index:
+                raise ValueError("device_ids %r does not match the module's device %s" % (device_ids, self.device))
+        self.broadcast_buffers = broadcast_buffers
+        if isinstance(comm, str):
+            comm = make_communicator(comm, group=process_group, device=self.device)
+        self.comm = comm
+        if wire_dtype is None:
+            wire_dtype = "bf16" if self.device.type == "cuda" else "fp32"
+        sync_module_states(module, comm, root=0)
+        self.engine = GradientEngine(params, comm, wire_dtype=wire_dtype, bucket_cap_mb=bucket_cap_mb, max_ctas=max_ctas,
+                                     check_inf=check_inf)
+        self._buffers_f = _float_buffers(module)
+
+    def forward(self, *inputs, **kwargs):
+        if self.broadcast_buffers and self.comm.world > 1 and self._buffers_f and torch.is_grad_enabled():
+            with torch.no_grad():
+                self.comm.broadcast_(self._buffers_f, root=0)
+        return self.module(*inputs, **kwargs)
+
+    @contextmanager
+    def no_sync(self):
+        old = self.engine.enabled
+        self.engine.enabled = False
+        try:
+            yield
+        finally:
+            self.engine.enabled = old
+
+    def state_dict(self, *args, **kwargs):  # keys carry the "module." prefix exactly like torch DDP
+        return super().state_dict(*args, **kwargs)

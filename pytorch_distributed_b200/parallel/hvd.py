@@ -1,0 +1,372 @@
+"""A from-scratch ``horovod.torch``-compatible module (the surface used by /root/reference/horovod_distributed.py).
+
+    import pytorch_distributed_b200.parallel.hvd as hvd
+    hvd.init(); hvd.local_rank(); hvd.size(); hvd.rank()                         (:125-127,147)
+    hvd.broadcast_parameters(model.state_dict(), root_rank=0)                    (:149)
+    hvd.broadcast_optimizer_state(optimizer, root_rank=0)                        (:158)
+    optimizer = hvd.DistributedOptimizer(optimizer, named_parameters=..., compression=hvd.Compression.fp16)  (:159-164)
+    hvd.allreduce(tensor, name='barrier')                                        (:104)
+
+Design (B200-native, not a horovod port):
+  * control plane: ``torch.distributed`` (env:// under torchrun, or the self-spawn launcher) - there is no MPI here;
+  * per-parameter hooks enqueue into the C++ :class:`FusionQueue` (``csrc/hvd_core.cpp``); a dispatcher thread pops
+    closed fusion groups and launches ONE fused cast(fp32->fp16 "compression") + all-reduce + decompress kernel per
+    group on a side stream - the fusion buffer IS the symmetric NVLink arena, so there is no copy-in/copy-out;
+  * ``optimizer.step()`` first ``synchronize()``s (flush + wait), exactly where horovod waits for its handles.
+Deviation: ``allreduce`` really returns the averaged tensor (the reference discards the return value).
+"""
+from __future__ import annotations
+
+import os
+import threading
+import time
+from typing import Dict, Iterable, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from ..utils.tensors import is_dense
+from .comm import KIND_TWO_SHOT, FusedCommunicator, make_communicator
+
+_state = {"init": False, "comm": None, "device": None, "handles": {}, "next": 1}
+_lock = threading.Lock()
+
+
+# ---------------------------------------------------------------------- basics
+def init(comm: Optional[str] = None, device: Optional[str] = None) -> None:
+    if _state["init"]:
+        return
+    use_cuda = torch.cuda.is_available() and (device is None or str(device).startswith("cuda"))
+    if not dist.is_initialized():
+        if "RANK" in os.environ and "WORLD_SIZE" in os.environ:
+            backend = "nccl" if use_cuda else "gloo"
+            if use_cuda:
+                torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+                dist.init_process_group(backend, device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))))
+            else:
+                dist.init_process_group(backend)
+    _state["device"] = torch.device("cuda", local_rank()) if use_cuda else torch.device("cpu")
+    if use_cuda:
+        torch.cuda.set_device(_state["device"])
+    _state["comm"] = make_communicator(comm or "auto", device=_state["device"])
+    _state["init"] = True
+
+
+def shutdown() -> None:
+    _state.update(init=False, comm=None)
+
+
+def is_initialized() -> bool:
+    return _state["init"]
+
+
+def size() -> int:
+    return dist.get_world_size() if dist.is_initialized() else 1
+
+
+def rank() -> int:
+    return dist.get_rank() if dist.is_initialized() else 0
+
+
+def local_rank() -> int:
+    return int(os.environ.get("LOCAL_RANK", rank() % max(1, torch.cuda.device_count() or 1)))
+
+
+def local_size() -> int:
+    return int(os.environ.get("LOCAL_WORLD_SIZE", size()))
+
+
+def communicator():
+    return _state["comm"]
+
+
+def nccl_built() -> bool:
+    return False      # the data plane is hand-written peer-memory kernels, not NCCL
+
+
+def mpi_enabled() -> bool:
+    return False
+
+
+class Compression:
+    """Wire formats of the fused all-reduce ("compression" = cast inside the kernel, no extra pass)."""
+
+    class none:  # noqa: N801
+        wire = None
+
+    class fp16:  # noqa: N801
+        wire = "fp16"
+
+    class bf16:  # noqa: N801
+        wire = "bf16"
+
+
+# ---------------------------------------------------------------------- tensor collectives
+def _wire_for(t: torch.Tensor, compression) -> Optional[str]:
+    w = getattr(compression, "wire", None)
+    if t.device.type != "cuda":
+        return None
+    return w
+
+
+def allreduce_(tensor: torch.Tensor, average: bool = True, name: Optional[str] = None, compression=Compression.none) -> torch.Tensor:
+    c = _state["comm"]
+    if c is None or c.world == 1:
+        return tensor
+    if tensor.dtype == torch.float32 and tensor.numel() <= 8 and isinstance(c, FusedCommunicator) and tensor.is_contiguous():
+        c.reduce_scalars_(tensor, average=average)     # latency path (metrics, "barrier" all-reduces)
+    else:
+        c.all_reduce_([tensor], average=average, wire=_wire_for(tensor, compression))
+    return tensor
+
+
+def allreduce(tensor: torch.Tensor, average: bool = True, name: Optional[str] = None, compression=Compression.none) -> torch.Tensor:
+    return allreduce_(tensor.clone(), average=average, name=name, compression=compression)
+
+
+def allreduce_async_(tensor: torch.Tensor, average: bool = True, name: Optional[str] = None) -> int:
+    """Stream-ordered: the collective is enqueued immediately; the handle carries an event."""
+    allreduce_(tensor, average=average, name=name)
+    ev = None
+    if tensor.is_cuda:
+        ev = torch.cuda.Event()
+        ev.record()
+    with _lock:
+        h = _state["next"]
+        _state["next"] += 1
+        _state["handles"][h] = (tensor, ev)
+    return h
+
+
+def allreduce_async(tensor, average=True, name=None) -> int:
+    return allreduce_async_(tensor.clone(), average=average, name=name)
+
+
+def poll(handle: int) -> bool:
+    t, ev = _state["handles"][handle]
+    return True if ev is None else ev.query()
+
+
+def synchronize(handle: int) -> torch.Tensor:
+    t, ev = _state["handles"].pop(handle)
+    if ev is not None:
+        torch.cuda.current_stream().wait_event(ev)
+    return t
+
+
+def broadcast_(tensor: torch.Tensor, root_rank: int, name: Optional[str] = None) -> torch.Tensor:
+    c = _state["comm"]
+    if c is not None and c.world > 1:
+        if tensor.is_floating_point():
+            c.broadcast_([tensor], root=root_rank)
+        else:
+            dist.broadcast(tensor, src=root_rank)
+    return tensor
+
+
+def broadcast(tensor, root_rank, name=None):
+    return broadcast_(tensor.clone(), root_rank, name)
+
+
+def broadcast_parameters(params, root_rank: int = 0) -> None:
+    """Accepts ``model.state_dict()`` or ``model.named_parameters()`` (horovod semantics)."""
+    c = _state["comm"]
+    if c is None or c.world == 1:
+        return
+    items = list(params.items()) if isinstance(params, dict) else list(params)
+    floats, others = [], []
+    for _, t in items:
+        if not torch.is_tensor(t):
+            continue
+        (floats if t.is_floating_point() else others).append(t.data if isinstance(t, torch.nn.Parameter) else t)
+    with torch.no_grad():
+        c.broadcast_(floats, root=root_rank)
+        for t in others:
+            dist.broadcast(t, src=root_rank)
+
+
+def broadcast_optimizer_state(optimizer, root_rank: int = 0) -> None:
+    """Scalars of the param groups and every tensor in ``optimizer.state`` follow rank ``root_rank``."""
+    c = _state["comm"]
+    if c is None or c.world == 1:
+        return
+    groups = [{k: v for k, v in g.items() if k != "params"} for g in optimizer.param_groups]
+    box = [groups]
+    dist.broadcast_object_list(box, src=root_rank)
+    for g, src in zip(optimizer.param_groups, box[0]):
+        g.update(src)
+    tensors = []
+    for g in optimizer.param_groups:
+        for p in g["params"]:
+            for v in optimizer.state.get(p, {}).values():
+                if torch.is_tensor(v) and v.is_floating_point():
+                    tensors.append(v)
+    if tensors:
+        c.broadcast_(tensors, root=root_rank)
+
+
+# ---------------------------------------------------------------------- DistributedOptimizer
+class _FusionEngine:
+    """Hooks -> C++ FusionQueue -> dispatcher thread -> fused all-reduce per fusion group."""
+
+    def __init__(self, named_params: Iterable[Tuple[str, torch.nn.Parameter]], comm, wire: Optional[str],
+                 fusion_threshold_mb: float, cycle_time_ms: float, backward_passes_per_step: int = 1):
+        from .. import _ext
+        self.comm = comm
+        self.fused = isinstance(comm, FusedCommunicator)
+        self.named = [(n, p) for n, p in named_params if p.requires_grad]
+        self.params = [p for _, p in self.named]
+        self.index = {id(p): i for i, p in enumerate(self.params)}
+        self.wire = wire
+        self.passes = backward_passes_per_step
+        self._counts = [0] * len(self.params)
+        self._handles: Dict[int, int] = {}          # queue handle -> param index
+        self._events: Dict[int, object] = {}
+        self._plans = {}                            # response cache: tuple(param ids) -> Plan
+        self._error = None
+        self.enabled = True
+        self.queue = None
+        self.thread = None
+        if comm.world > 1 or self.fused:
+            C = _ext.lib() if self.fused or _ext.available() else None
+            if C is not None:
+                self.queue = C.FusionQueue(int(fusion_threshold_mb * (1 << 20)), float(cycle_time_ms))
+        if self.fused:
+            self.stream = torch.cuda.Stream(device=comm.device, priority=-1)
+            self.channel = comm.new_channel()
+        if self.queue is not None:
+            self.thread = threading.Thread(target=self._dispatch_loop, name="ptd-hvd-cycle", daemon=True)
+            self.thread.start()
+        self._hooks = [p.register_post_accumulate_grad_hook(self._make_hook(i)) for i, p in enumerate(self.params)]
+
+    def _wire_bytes(self, p):
+        return p.numel() * (2 if self.wire in ("fp16", "bf16") else p.element_size())
+
+    def _make_hook(self, i):
+        def hook(param):
+            if not self.enabled or self.comm.world == 1 and not self.fused:
+                return
+            self._counts[i] += 1
+            if self._counts[i] < self.passes:
+                return
+            self._counts[i] = 0
+            if self.queue is None:
+                return
+            ev = None
+            if param.is_cuda:
+                ev = torch.cuda.Event()
+                ev.record()
+            h = self.queue.enqueue(self.named[i][0], self._wire_bytes(param), i)
+            with _lock:
+                self._handles[h] = i
+                self._events[h] = ev
+        return hook
+
+    def _launch_group(self, handles):
+        with _lock:
+            ids = [self._handles.pop(h) for h in handles]
+            evs = [self._events.pop(h) for h in handles]
+        grads = []
+        for i in ids:
+            g = self.params[i].grad
+            if not is_dense(g):
+                g = g.contiguous()
+                self.params[i].grad = g
+            grads.append(g)
+        if self.fused:
+            key = tuple(ids)
+            plan = self._plans.get(key)
+            wire = self.wire or ("fp32" if grads[0].dtype == torch.float32 else ("bf16" if grads[0].dtype == torch.bfloat16 else "fp16"))
+            if plan is None:
+                plan = self.comm.make_plan([g.numel() for g in grads], wire)
+                self._plans[key] = plan
+            if evs[-1] is not None:
+                self.stream.wait_event(evs[-1])     # events are stream-ordered: the last one covers the group
+            with torch.cuda.stream(self.stream):
+                self.comm.run(plan, grads, KIND_TWO_SHOT, self.channel, scale=1.0 / self.comm.world, writeback=True)
+        else:
+            self.comm.all_reduce_(grads, average=True, wire=self.wire)
+
+    def _dispatch_loop(self):
+        if self.fused:
+            torch.cuda.set_device(self.comm.device)
+        while True:
+            handles = self.queue.next_group(50.0)
+            if not handles:
+                if self._stop:
+                    return
+                continue
+            try:
+                self._launch_group(handles)
+            except Exception as e:  # noqa: BLE001 - surfaced by synchronize()
+                self._error = e
+            self.queue.mark_done(handles)
+
+    _stop = False
+
+    def synchronize(self):
+        """Flush the open fusion group, wait until every request has been launched, join the comm stream."""
+        if self.queue is None:
+            return
+        self.queue.flush()
+        while self.queue.pending() > 0:
+            if self._error is not None:
+                break
+            time.sleep(0.0002)
+        if self._error is not None:
+            e, self._error = self._error, None
+            raise e
+        if self.fused:
+            torch.cuda.current_stream().wait_stream(self.stream)
+
+    def close(self):
+        self._stop = True
+        if self.queue is not None:
+            self.queue.shutdown()
+        for h in self._hooks:
+            h.remove()
+
+
+def DistributedOptimizer(optimizer, named_parameters=None, compression=Compression.none, backward_passes_per_step: int = 1,
+                         op=None, fusion_threshold_mb: Optional[float] = None, cycle_time_ms: Optional[float] = None):
+    """Wrap ``optimizer`` so that ``step()`` first completes the asynchronous gradient all-reduces (horovod semantics).
+
+    Like horovod, this returns an instance of a dynamically created subclass of ``optimizer``'s class sharing its state.
+    """
+    if not _state["init"]:
+        init()
+    comm = _state["comm"]
+    if named_parameters is None:
+        named_parameters = [("param.%d" % i, p) for i, p in enumerate(p for g in optimizer.param_groups for p in g["params"])]
+    named_parameters = list(named_parameters)
+    names = [n for n, _ in named_parameters]
+    if len(set(names)) != len(names):
+        raise ValueError("named_parameters should consist of unique names")
+    thr = fusion_threshold_mb if fusion_threshold_mb is not None else float(os.environ.get("HOROVOD_FUSION_THRESHOLD", 64 << 20)) / (1 << 20)
+    cyc = cycle_time_ms if cycle_time_ms is not None else float(os.environ.get("HOROVOD_CYCLE_TIME", 5.0))
+    wire = getattr(compression, "wire", None)
+    if comm.device.type != "cuda":
+        wire = None
+    engine = _FusionEngine(named_parameters, comm, wire, thr, cyc, backward_passes_per_step)
+
+    base = optimizer.__class__
+
+    class _DistributedOptimizer(base):  # type: ignore[misc,valid-type]
+        def __init__(self):             # state is shared with the wrapped instance, not re-created
+            pass
+
+        def synchronize(self):
+            engine.synchronize()
+
+        def step(self, closure=None):
+            engine.synchronize()
+            return base.step(self, closure) if closure is not None else base.step(self)
+
+        def skip_synchronize(self):
+            import contextlib
+            return contextlib.nullcontext()
+
+    wrapped = _DistributedOptimizer.__new__(_DistributedOptimizer)
+    wrapped.__dict__ = optimizer.__dict__
+    wrapped._ptd_engine_obj = engine
+    return wrapped

@@ -1,0 +1,62 @@
+"""Checkpoint layout of the reference, plus an optional resume path.
+
+Reference: ``save_checkpoint`` /root/reference/distributed.py:327-330 and its call site :218-225 - files
+``checkpoint.pth.tar`` / ``model_best.pth.tar`` in the working directory, keys ``epoch`` (= epoch + 1), ``arch``,
+``state_dict`` (the *unwrapped* module), ``best_acc1``.  The state dict written here is always fp32, whatever
+precision the arenas / model copy run in.  ``--resume`` is an additive extension; optimizer and
+loss-scaler state ride along under extra keys that a reference-style reader simply ignores.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+
+import torch
+
+
+def export_state_dict(module: torch.nn.Module, engine=None):
+    """fp32 ``state_dict`` of the unwrapped module; master weights replace low-precision model copies."""
+    sd = module.state_dict()
+    masters = {}
+    if engine is not None and hasattr(engine, "master_params"):
+        idx = {id(p): i for i, p in enumerate(engine.params)}
+        mp = engine.master_params()
+        for name, p in module.named_parameters():
+            if id(p) in idx:
+                masters[name] = mp[idx[id(p)]]
+    out = type(sd)()
+    for k, v in sd.items():
+        v = masters.get(k, v)
+        if torch.is_tensor(v):
+            v = v.detach()
+            if v.is_floating_point() and v.dtype != torch.float32:
+                v = v.float()
+            v = v.cpu().contiguous().clone()
+        out[k] = v
+    return out
+
+
+def save_checkpoint(state, is_best: bool, filename: str = "checkpoint.pth.tar", directory: str = ".") -> str:
+    path = os.path.join(directory, filename)
+    torch.save(state, path)
+    if is_best:
+        shutil.copyfile(path, os.path.join(directory, "model_best.pth.tar"))
+    return path
+
+
+def load_checkpoint(path: str, module: torch.nn.Module, optimizer=None, map_location="cpu"):
+    ckpt = torch.load(path, map_location=map_location, weights_only=False)
+    sd = ckpt["state_dict"]
+    if all(k.startswith("module.") for k in sd):
+        sd = {k[len("module."):]: v for k, v in sd.items()}
+    with torch.no_grad():
+        own = module.state_dict()
+        for k, v in sd.items():
+            if k in own:
+                own[k].copy_(v.to(own[k].dtype))
+    if optimizer is not None and "optimizer" in ckpt:
+        try:
+            optimizer.load_state_dict(ckpt["optimizer"])
+        except Exception as e:  # noqa: BLE001
+            print("=> optimizer state not restored (%s)" % (e,))
+    return ckpt
