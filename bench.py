@@ -1,0 +1,265 @@
+"""Headline benchmark: ResNet-50 training images/sec on N B200s (BASELINE.json metric / config).
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port P bench.py --gpus 8 ...
+    python bench.py --impl reference ...        (the unmodified reference scripts from baseline/_ref, stock code path)
+
+Own arm: the public training path of this repo (driver.Strategy.build -> DistributedDataParallel + FusedSGD, the
+DataPrefetcher, the MetricPipeline) - the same objects `distributed.py` uses.
+  value       device-timed (CUDA events, max over ranks) images/s of K full training steps
+              (forward + loss + metric kernel + backward with fused all-reduce + optimizer), inputs already on the
+              device (4 distinct 256-image bf16 NHWC batches = 154 MB > the 126 MB L2; activations are GBs).
+  e2e.value   the same loop fed from PINNED HOST memory through the prefetcher (H2D of every batch inside the timed
+              region) with the step's reduced loss/accuracy copied back to the host every step.
+Synthetic data, random-init weights, weak scaling (256 images per GPU).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ResNet-50 images/sec (device-timed, max over ranks)"
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=20)
+    p.add_argument("--warmup", type=int, default=5)
+    p.add_argument("--impl", default="own", choices=["own", "reference"])
+    p.add_argument("--arch", default="resnet50")
+    p.add_argument("--batch-per-gpu", type=int, default=256)
+    p.add_argument("--precision", default="bf16")
+    p.add_argument("--comm", default="auto")
+    p.add_argument("--no-fused-bn", action="store_true")
+    p.add_argument("--optimizer", default="fused")
+    p.add_argument("--skip-e2e", action="store_true")
+    p.add_argument("--entry", default="distributed", choices=["distributed", "apex_distributed", "horovod_distributed"])
+    p.add_argument("--opt-level", default="O2")
+    return p.parse_args()
+
+
+# ---------------------------------------------------------------------- clocks sampling (rank 0)
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int = 0):
+        self.samples = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_env():
+    if "RANK" in os.environ and "WORLD_SIZE" in os.environ:
+        return int(os.environ["RANK"]), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ["WORLD_SIZE"])
+    return 0, 0, 1
+
+
+def max_over_ranks(ms: float, device) -> float:
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    return ms
+
+
+def barrier_sync(device):
+    torch.cuda.synchronize(device)
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.barrier()
+    torch.cuda.synchronize(device)
+
+
+# ====================================================================== own arm
+def run_own(a):
+    from pytorch_distributed_b200 import _ext, cli, driver
+    from pytorch_distributed_b200.models import create_model
+    from pytorch_distributed_b200.utils.data import SyntheticLoader
+    from pytorch_distributed_b200.utils.meters import AverageMeter
+
+    rank, local_rank, world = dist_env()
+    assert world == a.gpus or world == 1, "launch with torchrun --nproc-per-node %d" % a.gpus
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    argv = ["-a", a.arch, "-b", str(a.batch_per_gpu * world), "--synthetic", "--precision", a.precision, "--comm", a.comm,
+            "--optimizer", a.optimizer, "--quiet"]
+    if a.no_fused_bn:
+        argv.append("--no-fused-bn")
+    if a.entry == "apex_distributed":
+        argv += ["--opt-level", a.opt_level]
+        if a.precision == "bf16":
+            argv[argv.index("--precision") + 1] = "fp16"
+    args = cli.parse_args(a.entry, argv)
+    st = driver.STRATEGIES[a.entry]()
+    if world > 1 or a.entry == "horovod_distributed":
+        st.init_process_group(args, local_rank, world)
+    model = create_model(args.arch, num_classes=args.num_classes, fused_bn=args.fused_bn)
+    model, optimizer = st.build(model, args, device, local_rank)
+    criterion = torch.nn.CrossEntropyLoss().to(device)
+    torch.backends.cudnn.benchmark = True
+    B = a.batch_per_gpu
+    W, K = a.warmup, a.steps
+    losses, top1, top5 = AverageMeter("Loss"), AverageMeter("Acc@1"), AverageMeter("Acc@5")
+    metrics = driver.MetricPipeline(getattr(st, "comm", None), device, (losses, top1, top5), reduce=True)
+
+    def step(images, target):
+        output = st.forward(model, images)
+        loss = criterion(output.float() if output.dtype != torch.float32 else output, target)
+        metrics.push(output, target, loss, images.size(0))
+        optimizer.zero_grad()
+        st.backward(loss, optimizer)
+        optimizer.step()
+        metrics.poll()
+
+    model.train()
+    # ---------------- phase A: device-resident inputs (the `value`)
+    loader = SyntheticLoader(B, 4, args.image_size, args.num_classes, pool=4, rank=rank)
+    pf = st.prefetcher(loader, device, args)
+    resident = [(i.clone(), t.clone()) for i, t in pf]      # 4 distinct bf16 NHWC batches, staged once
+    torch.cuda.synchronize(device)
+    for i in range(W):
+        step(*resident[i % len(resident)])
+    metrics.drain()
+    barrier_sync(device)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    n0 = _ext.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(K):
+        step(*resident[i % len(resident)])
+    ev1.record()
+    barrier_sync(device)
+    launches = _ext.launches - n0
+    clocks = sampler.stop() if rank == 0 else None
+    metrics.drain()
+    ms = max_over_ranks(ev0.elapsed_time(ev1), device)
+    value = B * world * K / (ms / 1e3)
+
+    # ---------------- phase B: end to end (pinned host -> device every step, metrics back to the host every step)
+    e2e = None
+    if not a.skip_e2e:
+        loader = SyntheticLoader(B, W + K, args.image_size, args.num_classes, pool=4, rank=rank)
+        pf = st.prefetcher(loader, device, args)
+        it = iter(pf)
+        for _ in range(W):
+            step(*next(it))
+        metrics.drain()
+        barrier_sync(device)
+        h0, d0 = pf.h2d_bytes, metrics.d2h_bytes
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        n = 0
+        for batch in it:
+            step(*batch)
+            n += 1
+        metrics.drain()                     # the host has read every step's loss/accuracy
+        e1.record()
+        barrier_sync(device)
+        assert n == K, (n, K)
+        ms2 = max_over_ranks(e0.elapsed_time(e1), device)
+        # the prefetcher stages batch i+1 while step i runs: K-1 copies + the first timed batch (staged during the
+        # last warm-up step) => count K copies for K steps.
+        e2e = {"value": B * world * K / (ms2 / 1e3), "unit": "images/s", "ms_per_step": ms2 / K,
+               "h2d_bytes_per_step": loader.bytes_per_step, "d2h_bytes_per_step": (metrics.d2h_bytes - d0) // max(K, 1)}
+    comm = getattr(st, "comm", None)
+    if comm is not None:
+        comm.check()
+    if rank == 0:
+        base = published_baseline()
+        out = {
+            "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": (value / base) if base else None, "dtype": args.precision, "data": "synthetic",
+            "config": {"model": a.arch, "global_batch": B * world, "seq_len": None, "image_size": args.image_size,
+                       "parallelism": "dp%d" % world, "entry": a.entry, "comm": getattr(comm, "backend", "none"),
+                       "nvls": bool(getattr(comm, "nvls", False)), "channels_last": bool(args.channels_last),
+                       "fused_bn": args.fused_bn is not False, "optimizer": a.optimizer,
+                       "l2_policy": "inputs larger than L2 (4 x 38.5 MB bf16 batches + GBs of activations per step)"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "impl": "own",
+            "final_loss": losses.val,
+        }
+        print(json.dumps(out), flush=True)
+    if dist.is_initialized():
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def published_baseline():
+    try:
+        with open(os.path.join(ROOT, "BASELINE.json")) as f:
+            pub = json.load(f).get("published", {})
+        for v in pub.values():
+            if isinstance(v, (int, float)):
+                return float(v)
+    except Exception:  # noqa: BLE001
+        pass
+    return None
+
+
+# ====================================================================== reference arm
+def run_reference(a):
+    from baseline.run_reference import run
+    run(a, METRIC, ClockSampler, published_baseline)
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_own(a)

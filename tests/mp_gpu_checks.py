@@ -1,0 +1,138 @@
+"""Multi-GPU checks, launched by tests/test_gpu_multi.py (or by hand) under torchrun; every rank must print PASS.
+
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/mp_gpu_checks.py
+"""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    from pytorch_distributed_b200.parallel.comm import KIND_ONE_SHOT, KIND_TWO_SHOT, FusedCommunicator
+    nvls_env = os.environ.get("PTD_NVLS", "1")
+    comm = FusedCommunicator(device=dev, arena_bytes=256 << 20, timeout_ms=20000)
+    if rank == 0:
+        print("[info] world=%d symm=%s nvls=%s (PTD_NVLS=%s) mc_error=%r" % (world, comm.symm_backend, comm.nvls, nvls_env, comm.arena.mc_error), flush=True)
+    torch.manual_seed(1234 + rank)
+
+    # ---- K3 barrier, many iterations
+    for _ in range(200):
+        comm.barrier()
+    torch.cuda.synchronize()
+    comm.check()
+
+    # ---- K1 two-shot / one-shot vs NCCL, odd sizes, mixed dtypes, all wire formats, both NVLS and P2P
+    shapes = [(64, 3, 7, 7), (64,), (5,), (1000, 2048), (2048,), (33, 17), (1,), (3000001,)]
+    for wire, tol in (("fp32", 1e-5), ("bf16", 3e-2), ("fp16", 4e-3)):
+        for kind in (KIND_TWO_SHOT, KIND_ONE_SHOT):
+            for nvls in ((True, False) if comm.nvls else (False,)):
+                ts = [torch.randn(s, device=dev) for s in shapes]
+                ts[3] = ts[3].bfloat16() if wire != "fp16" else ts[3].half()
+                ref = []
+                for t in ts:
+                    r = t.float().clone()
+                    dist.all_reduce(r)
+                    ref.append(r / world)
+                plan = comm.make_plan([t.numel() for t in ts], wire, double_buffer=(kind == KIND_ONE_SHOT))
+                for rep in range(3):        # repeated launches exercise flag reuse / double buffering
+                    work = [t.clone() for t in ts]
+                    comm.run(plan, work, kind, comm.misc_channel, scale=1.0 / world, writeback=True, nvls=nvls)
+                torch.cuda.synchronize()
+                comm.check()
+                for w, r in zip(work, ref):
+                    err = (w.float() - r).abs().max().item()
+                    lim = tol * max(1.0, r.abs().max().item())
+                    assert err <= lim, "allreduce wire=%s kind=%d nvls=%s: err %g > %g" % (wire, kind, nvls, err, lim)
+
+    # ---- generic API: all_reduce_ (small => one-shot, large => two-shot), broadcast_
+    a = torch.full((10,), float(rank + 1), device=dev)
+    big = torch.full((1 << 20,), float(rank + 1), device=dev)
+    comm.all_reduce_([a], average=False)
+    comm.all_reduce_([big], average=True)
+    torch.cuda.synchronize()
+    assert torch.allclose(a, torch.full_like(a, world * (world + 1) / 2)), a
+    assert torch.allclose(big, torch.full_like(big, (world + 1) / 2)), big[:4]
+    for root in range(world):
+        for rep in range(3):
+            t1 = torch.full((1000, 37), float(rank * 10 + rep), device=dev)
+            t2 = torch.full((13,), float(rank) + 0.5, device=dev).bfloat16()
+            comm.broadcast_([t1, t2], root=root)
+            torch.cuda.synchronize()
+            assert torch.all(t1 == float(root * 10 + rep)) and torch.all(t2.float() == root + 0.5), (root, rep, t1[0, 0].item())
+    comm.check()
+
+    # ---- K4 metrics + LL all-reduce, many back-to-back calls (parity reuse)
+    from pytorch_distributed_b200.utils.meters import accuracy
+    out = torch.zeros(4, device=dev)
+    for it in range(50):
+        logits = torch.randn(64, 1000, device=dev).bfloat16()
+        target = torch.randint(0, 1000, (64,), device=dev)
+        logits[torch.arange(10 + rank), target[:10 + rank]] += 30
+        loss = torch.tensor(float(rank + it), device=dev)
+        comm.metrics(logits, target, loss, out)
+        a1, a5 = accuracy(logits, target, (1, 5))
+        exp = torch.stack([loss, a1[0], a5[0]])
+        dist.all_reduce(exp)
+        exp /= world
+        torch.cuda.synchronize()
+        assert torch.allclose(out[:3], exp, atol=1e-3), (it, out, exp)
+        s = torch.tensor([1.0 * rank, 2.0, -3.0 * rank], device=dev)
+        comm.reduce_scalars_(s, average=True)
+        torch.cuda.synchronize()
+        assert abs(s[0].item() - (world - 1) / 2) < 1e-5 and abs(s[1].item() - 2.0) < 1e-6, s
+    comm.check()
+
+    # ---- DDP: fused engine == torch DDP (NCCL) gradients, fp32 wire (tight) and bf16 wire (loose); flat optimizer parity
+    import copy
+    from pytorch_distributed_b200.models import create_model
+    from pytorch_distributed_b200.ops.fused_sgd import FusedSGD
+    from pytorch_distributed_b200.parallel.ddp import DistributedDataParallel
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    for wire, tol in (("fp32", 2e-4), ("bf16", 3e-2)):
+        torch.manual_seed(7)
+        base = create_model("resnet18", num_classes=10, fused_bn=False).to(dev)
+        m_ref = torch.nn.parallel.DistributedDataParallel(copy.deepcopy(base), device_ids=[local])
+        m_own = DistributedDataParallel(copy.deepcopy(base), device_ids=[local], comm=comm, wire_dtype=wire)
+        o_ref = torch.optim.SGD(m_ref.parameters(), lr=0.05, momentum=0.9, weight_decay=1e-4)
+        o_own = FusedSGD(m_own.parameters(), lr=0.05, momentum=0.9, weight_decay=1e-4)
+        assert o_own.is_flat
+        crit = torch.nn.CrossEntropyLoss()
+        torch.manual_seed(100 + rank)
+        for it in range(3):
+            x = torch.randn(8, 3, 64, 64, device=dev)
+            y = torch.randint(0, 10, (8,), device=dev)
+            for m, o in ((m_ref, o_ref), (m_own, o_own)):
+                o.zero_grad()
+                crit(m(x), y).backward()
+                o.step()
+        torch.cuda.synchronize()
+        comm.check()
+        for (n1, p1), (n2, p2) in zip(m_ref.module.named_parameters(), m_own.module.named_parameters()):
+            err = (p1 - p2).abs().max().item()
+            lim = tol * max(1.0, p1.abs().max().item())
+            assert err <= lim, "DDP parity wire=%s %s: %g > %g" % (wire, n1, err, lim)
+        # every rank holds identical weights
+        flat = torch.cat([p.detach().reshape(-1) for p in m_own.parameters()])
+        lo, hi = flat.clone(), flat.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        assert torch.equal(lo, hi), "ranks diverged"
+        m_own.engine.remove_hooks()
+
+    dist.barrier()
+    print("PASS rank %d" % rank, flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
