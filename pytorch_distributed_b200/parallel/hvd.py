@@ -17,6 +17,7 @@ Deviation: ``allreduce`` really returns the averaged tensor (the ref
 """
 from __future__ import annotations
 
+import atexit
 import os
 import threading
 import time
@@ -237,6 +238,7 @@ class _FusionEngine:
         if self.queue is not None:
             self.thread = threading.Thread(target=self._dispatch_loop, name="ptd-hvd-cycle", daemon=True)
             self.thread.start()
+            atexit.register(self.close)     # the thread must leave the C++ wait before the interpreter finalises
         self._hooks = [p.register_post_accumulate_grad_hook(self._make_hook(i)) for i, p in enumerate(self.params)]
 
     def _wire_bytes(self, p):
@@ -323,8 +325,12 @@ class _FusionEngine:
         self._stop = True
         if self.queue is not None:
             self.queue.shutdown()
+        if self.thread is not None and self.thread.is_alive() and threading.current_thread() is not self.thread:
+            self.thread.join(timeout=5.0)
+        self.thread = None
         for h in self._hooks:
             h.remove()
+        self._hooks = []
 
 
 def DistributedOptimizer(optimizer, named_parameters=None, compression=Compression.none, backward_passes_per_step: int = 1,

@@ -50,7 +50,8 @@ def main():
                 comm.check()
                 for w, r in zip(work, ref):
                     err = (w.float() - r).abs().max().item()
-                    lim = tol * max(1.0, r.abs().max().item())
+                    t_eff = max(tol, {torch.bfloat16: 1e-2, torch.float16: 2e-3}.get(w.dtype, 0.0))   # destination rounding
+                    lim = t_eff * max(1.0, r.abs().max().item())
                     assert err <= lim, "allreduce wire=%s kind=%d nvls=%s: err %g > %g" % (wire, kind, nvls, err, lim)
 
     # ---- generic API: all_reduce_ (small => one-shot, large => two-shot), broadcast_
@@ -111,16 +112,31 @@ def main():
         for it in range(3):
             x = torch.randn(8, 3, 64, 64, device=dev)
             y = torch.randint(0, 10, (8,), device=dev)
+            # Same weights / buffers going into every iteration: this net at batch 8 amplifies 1e-8 differences by
+            # orders of magnitude per step, so the comparison is per iteration, not of whole trajectories.
+            with torch.no_grad():
+                for pa, pb in zip(m_ref.module.parameters(), m_own.module.parameters()):
+                    pa.copy_(pb)
+                for pa, pb in zip(m_ref.module.buffers(), m_own.module.buffers()):
+                    pa.copy_(pb)
+                if it > 0:
+                    for pa, pb in zip(m_ref.module.parameters(), m_own.module.parameters()):
+                        o_ref.state[pa]["momentum_buffer"].copy_(o_own.state[pb]["momentum_buffer"])
             for m, o in ((m_ref, o_ref), (m_own, o_own)):
                 o.zero_grad()
                 crit(m(x), y).backward()
                 o.step()
-        torch.cuda.synchronize()
-        comm.check()
-        for (n1, p1), (n2, p2) in zip(m_ref.module.named_parameters(), m_own.module.named_parameters()):
-            err = (p1 - p2).abs().max().item()
-            lim = tol * max(1.0, p1.abs().max().item())
-            assert err <= lim, "DDP parity wire=%s %s: %g > %g" % (wire, n1, err, lim)
+            torch.cuda.synchronize()
+            comm.check()
+            arena = m_own.engine.grad_arena()
+            for i, ((n1, p1), p2) in enumerate(zip(m_ref.module.named_parameters(), m_own.engine.params)):
+                off = m_own.engine.param_elem_off[i]
+                gerr = (arena[off:off + p2.numel()].view_as(p1).float() - p1.grad).abs().max().item()
+                glim = tol * max(1e-3, p1.grad.abs().max().item())
+                assert gerr <= glim, "DDP grad parity wire=%s it=%d %s: %g > %g" % (wire, it, n1, gerr, glim)
+                err = (p1 - p2).abs().max().item()
+                lim = tol * 0.05 * max(1e-3, p1.grad.abs().max().item()) * 4 + 1e-6
+                assert err <= lim, "DDP param parity wire=%s it=%d %s: %g > %g" % (wire, it, n1, err, lim)
         # every rank holds identical weights
         flat = torch.cat([p.detach().reshape(-1) for p in m_own.parameters()])
         lo, hi = flat.clone(), flat.clone()

@@ -152,7 +152,8 @@ def test_normalize_kernel(src_dtype, out):
     ref = src.float() * a.view(1, 3, 1, 1) + b.view(1, 3, 1, 1)
     assert y.dtype == odt and y.shape == src.shape
     assert y.is_contiguous(memory_format=torch.channels_last if cl else torch.contiguous_format)
-    torch.testing.assert_close(y.float(), ref.to(odt).float(), rtol=0, atol=0)
+    tol = 1e-5 if odt == torch.float32 else 1e-2      # kernel uses one FMA; the oracle rounds the product first
+    torch.testing.assert_close(y.float(), ref.to(odt).float(), rtol=tol, atol=tol)
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
