@@ -179,10 +179,16 @@ def run_own(a):
         sampler.start()
     n0 = _ext.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    prof = os.environ.get("PTD_PROFILE") == "1"     # ncu --profile-from-start off: capture only the timed region
+    if prof:
+        torch.cuda.profiler.start()
     ev0.record()
     for i in range(K):
         step(*resident[i % len(resident)])
     ev1.record()
+    if prof:
+        torch.cuda.synchronize(device)
+        torch.cuda.profiler.stop()
     barrier_sync(device)
     launches = _ext.launches - n0
     clocks = sampler.stop() if rank == 0 else None
