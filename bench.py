@@ -183,8 +183,10 @@ def run_own(a):
     if prof:
         torch.cuda.profiler.start()
     ev0.record()
+    t_host = time.perf_counter()
     for i in range(K):
         step(*resident[i % len(resident)])
+    host_ms = (time.perf_counter() - t_host) * 1e3 / K      # time the host needs to ENQUEUE one step
     ev1.record()
     if prof:
         torch.cuda.synchronize(device)
@@ -236,7 +238,7 @@ def run_own(a):
                        "nvls": bool(getattr(comm, "nvls", False)), "channels_last": bool(args.channels_last),
                        "fused_bn": args.fused_bn is not False, "optimizer": a.optimizer,
                        "l2_policy": "inputs larger than L2 (4 x 38.5 MB bf16 batches + GBs of activations per step)"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "impl": "own",
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "impl": "own", "host_enqueue_ms_per_step": host_ms,
             "final_loss": losses.val,
         }
         print(json.dumps(out), flush=True)

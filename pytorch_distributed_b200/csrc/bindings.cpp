@@ -92,6 +92,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("amp_update_scale", &amp_update_scale);
   m.def("bn_act_forward", &bn_act_forward);
   m.def("bn_act_backward", &bn_act_backward);
+  m.def("stem_forward", &stem_forward);
+  m.def("stem_backward", &stem_backward);
   m.def("normalize_nhwc", &normalize_nhwc);
   m.def("p2p_copy_multi", &p2p_copy_multi);
 

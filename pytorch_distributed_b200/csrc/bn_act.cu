@@ -2,12 +2,16 @@
 //
 // The reference reaches cuDNN BN + ATen add + ATen ReLU through torchvision's ResNet
 // (/root/reference/distributed.py:136-139,250).  On B200 a bf16 ResNet-50 step is bound by exactly those
-// memory passes, so they are fused here:
-//   forward : stats pass (1 read)  + apply pass  (x [+res] -> y : 1-2 reads, 1 write)       eager: 3-5 R, 2-3 W
-//   backward: reduce pass (dy,y,x) + apply pass  (dy,y,x -> dx [,dres])                      eager: 6 R, 2-3 W
+// memory passes (45% of the step in the first profile, profiles/step_breakdown_r1.md), so they are fused here:
+//   forward : stats pass (1 read)  + apply pass  (x [+res] -> y, 1-bit ReLU mask)             eager: 3-5 R, 2-3 W
+//   backward: reduce pass (dy,x,mask) + apply pass (dy,x,mask -> dx [,dres])                   eager: 6 R, 2-3 W
+// The ReLU decision is kept as ONE BIT per element (a byte per thread-vector of 8 channels), so the backward never
+// re-reads the 16-bit output tensor: 4.125 B/element per backward pass instead of 6.
 // Layout: activations are channels_last, i.e. a row-major [M = N*H*W, C] matrix.  A thread owns 8 consecutive
 // channels (one 16-byte vector for 16-bit dtypes) and walks down the rows, so every warp access is a fully
 // coalesced 128..512-byte line and the per-channel reductions stay in registers until the end of the CTA.
+// CTA-level combine: warp shuffles (lanes sharing a channel group) -> one shared-memory row per warp/row-group
+// (plain stores, no shared atomics) -> one fire-and-forget global fp32 RED per (CTA, channel).
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>
 #include <torch/extension.h>
@@ -18,14 +22,16 @@
 namespace ptd {
 
 constexpr int kBnThreads = 256;
+constexpr int kBnWarps = kBnThreads / 32;
 
 struct RowMap {
   int cgs;     // channel groups (C / 8)
-  int tpr;     // threads per row
+  int tpr;     // threads per row (power of two <= 256, or cgs when cgs < 256 and not a power of two)
   int rpp;     // rows per pass of one CTA
   int rlocal;  // this thread's row inside a pass
   int cg0;     // this thread's first channel group
   bool active;
+  bool pow2;
 };
 __device__ __forceinline__ RowMap row_map(int C) {
   RowMap m;
@@ -35,6 +41,7 @@ __device__ __forceinline__ RowMap row_map(int C) {
   m.rlocal = threadIdx.x / m.tpr;
   m.cg0 = threadIdx.x % m.tpr;
   m.active = m.rlocal < m.rpp;
+  m.pow2 = (m.tpr & (m.tpr - 1)) == 0;
   return m;
 }
 
@@ -53,10 +60,14 @@ __device__ __forceinline__ void st_w(void* p, int dt, int i, float v) {
   }
 }
 
-// Flush per-thread channel partials: lanes of a warp that share a channel group are combined by shuffles,
-// then one shared-memory atomic per (warp, channel), then one global atomic per (CTA, channel).
-__device__ __forceinline__ void flush_partials(const RowMap& m, int cg, float (&a)[8], float (&b)[8], float* sm, int C) {
-  if (m.tpr < 32 && (m.tpr & (m.tpr - 1)) == 0) {
+// Combine the per-thread partial sums (a[8], b[8] for channel group `cg`) of a CTA into gsum[0:C] / gsum[C:2C].
+// Caller loops over channel-group chunks; `sm` holds [slots][2 * tpr * 8] floats.
+__device__ __forceinline__ void cta_combine(const RowMap& m, int cg_base, float (&a)[8], float (&b)[8], float* sm, float* gsum, int C) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int width = m.tpr * 8;        // channels covered per pass
+  int slots, slot;
+  bool writer = m.active;
+  if (m.pow2 && m.tpr < 32) {         // several rows share a warp: fold them with shuffles first
     for (int o = m.tpr; o < 32; o <<= 1) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
@@ -64,12 +75,25 @@ __device__ __forceinline__ void flush_partials(const RowMap& m, int cg, float (&
         b[k] += __shfl_xor_sync(0xffffffffu, b[k], o);
       }
     }
-    if ((threadIdx.x & 31) >= m.tpr) return;
+    slots = kBnWarps;
+    slot = warp;
+    writer = lane < m.tpr;
+  } else {
+    slots = m.rpp;
+    slot = m.rlocal;
   }
+  __syncthreads();                    // previous chunk's readers are done with sm
+  if (writer) {
+    float* row = sm + (size_t)slot * 2 * width + m.cg0 * 8;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    atomicAdd(&sm[cg * 8 + k], a[k]);
-    atomicAdd(&sm[C + cg * 8 + k], b[k]);
+    for (int k = 0; k < 8; ++k) { row[k] = a[k]; row[width + k] = b[k]; }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * width; i += blockDim.x) {
+    float s = 0.f;
+    for (int r = 0; r < slots; ++r) s += sm[(size_t)r * 2 * width + i];
+    const int half = i >= width, c = cg_base * 8 + (i - half * width);
+    if (c < C) atomicAdd(&gsum[half * C + c], s);
   }
 }
 
@@ -78,51 +102,47 @@ template <typename T>
 __global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const T* __restrict__ x, float* __restrict__ gsum, int64_t M, int C,
                                                               int rows_per_block) {
   extern __shared__ float sm[];
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
-  __syncthreads();
   const RowMap m = row_map(C);
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = min(M, r0 + (int64_t)rows_per_block);
-  const bool warp_uniform = (m.tpr >= 32) || ((m.tpr & (m.tpr - 1)) == 0);
-  if (m.active || warp_uniform) {
-    for (int cg = m.cg0; cg < m.cgs; cg += m.tpr) {
-      float s[8], q[8];
+  for (int cgb = 0; cgb < m.cgs; cgb += m.tpr) {
+    const int cg = cgb + m.cg0;
+    float s[8], q[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) { s[k] = 0.f; q[k] = 0.f; }
-      if (m.active) {
-        const T* p = x + cg * 8;
-        int64_t r = r0 + m.rlocal;
-        for (; r + 3 * (int64_t)m.rpp < r1; r += 4 * (int64_t)m.rpp) {
-          float f[4][8];
+    for (int k = 0; k < 8; ++k) { s[k] = 0.f; q[k] = 0.f; }
+    if (m.active && cg < m.cgs) {
+      const T* p = x + cg * 8;
+      int64_t r = r0 + m.rlocal;
+      for (; r + 7 * (int64_t)m.rpp < r1; r += 8 * (int64_t)m.rpp) {
+        float f[8][8];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) load8<T>(p + (r + (int64_t)u * m.rpp) * C, f[u]);
+        for (int u = 0; u < 8; ++u) load8<T>(p + (r + (int64_t)u * m.rpp) * C, f[u]);
 #pragma unroll
-          for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < 8; ++u)
 #pragma unroll
-            for (int k = 0; k < 8; ++k) { s[k] += f[u][k]; q[k] += f[u][k] * f[u][k]; }
-        }
-        for (; r < r1; r += m.rpp) {
-          float f[8];
-          load8<T>(p + r * C, f);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) { s[k] += f[k]; q[k] += f[k] * f[k]; }
-        }
+          for (int k = 0; k < 8; ++k) { s[k] += f[u][k]; q[k] += f[u][k] * f[u][k]; }
       }
-      flush_partials(m, cg, s, q, sm, C);
+      for (; r < r1; r += m.rpp) {
+        float f[8];
+        load8<T>(p + r * C, f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { s[k] += f[k]; q[k] += f[k] * f[k]; }
+      }
     }
+    cta_combine(m, cgb, s, q, sm, gsum, C);
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&gsum[i], sm[i]);
 }
 
 // ------------------------------------------------------------------ forward: normalise (+res) (+relu)
 template <typename T, bool RELU, bool RES>
 __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __restrict__ y,
-                                                              const float* __restrict__ gsum, const void* __restrict__ w,
-                                                              const void* __restrict__ b, int wdt, float* __restrict__ running_mean,
-                                                              float* __restrict__ running_var, float* __restrict__ saved, int64_t M, int C,
-                                                              float eps, float momentum, int training) {
+                                                              uint8_t* __restrict__ mask, const float* __restrict__ gsum,
+                                                              const void* __restrict__ w, const void* __restrict__ b, int wdt,
+                                                              float* __restrict__ running_mean, float* __restrict__ running_var,
+                                                              int64_t* __restrict__ num_batches_tracked, float* __restrict__ saved,
+                                                              int64_t M, int C, float eps, float momentum, int training) {
   const RowMap m = row_map(C);
   const float inv_m = 1.f / (float)M;
+  if (training && num_batches_tracked && blockIdx.x == 0 && threadIdx.x == 0) *num_batches_tracked += 1;
   if (!m.active) return;
   for (int cg = m.cg0; cg < m.cgs; cg += m.tpr) {
     float sc[8], sh[8];
@@ -163,114 +183,119 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const T* __restric
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
+        unsigned bits = 0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           float v = f[u][k] * sc[k] + sh[k];
           if constexpr (RES) v += g[u][k];
-          if constexpr (RELU) v = fmaxf(v, 0.f);
+          if constexpr (RELU) { bits |= (v > 0.f ? 1u : 0u) << k; v = fmaxf(v, 0.f); }
           f[u][k] = v;
         }
         store8<T>(y + (r + u * stride) * C + coff, f[u]);
+        if constexpr (RELU) { if (mask) mask[(r + u * stride) * m.cgs + cg] = (uint8_t)bits; }
       }
     }
     for (; r < M; r += stride) {
       float f[8], g[8];
       load8<T>(x + r * C + coff, f);
       if constexpr (RES) load8<T>(res + r * C + coff, g);
+      unsigned bits = 0;
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         float v = f[k] * sc[k] + sh[k];
         if constexpr (RES) v += g[k];
-        if constexpr (RELU) v = fmaxf(v, 0.f);
+        if constexpr (RELU) { bits |= (v > 0.f ? 1u : 0u) << k; v = fmaxf(v, 0.f); }
         f[k] = v;
       }
       store8<T>(y + r * C + coff, f);
+      if constexpr (RELU) { if (mask) mask[r * m.cgs + cg] = (uint8_t)bits; }
     }
   }
 }
 
 // ------------------------------------------------------------------ backward: reductions
-// gsum[0:C] = sum dz ; gsum[C:2C] = sum dz * xhat   with dz = dy * (y > 0) when RELU
+// gsum[0:C] = sum dz ; gsum[C:2C] = sum dz * xhat   with dz = dy * relu_mask
 template <typename T, bool RELU>
-__global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ y, const T* __restrict__ x,
-                                                                   const float* __restrict__ saved, float* __restrict__ gsum, int64_t M, int C,
-                                                                   int rows_per_block) {
+__global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ mask,
+                                                                   const T* __restrict__ x, const float* __restrict__ saved,
+                                                                   float* __restrict__ gsum, int64_t M, int C, int rows_per_block) {
   extern __shared__ float sm[];
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
-  __syncthreads();
   const RowMap m = row_map(C);
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = min(M, r0 + (int64_t)rows_per_block);
-  const bool warp_uniform = (m.tpr >= 32) || ((m.tpr & (m.tpr - 1)) == 0);
-  if (m.active || warp_uniform) {
-    for (int cg = m.cg0; cg < m.cgs; cg += m.tpr) {
-      float s[8], q[8], mean[8], invstd[8];
+  for (int cgb = 0; cgb < m.cgs; cgb += m.tpr) {
+    const int cg = cgb + m.cg0;
+    float s[8], q[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) { s[k] = 0.f; q[k] = 0.f; mean[k] = saved[cg * 8 + k]; invstd[k] = saved[C + cg * 8 + k]; }
-      if (m.active) {
-        const int64_t coff = cg * 8;
-        int64_t r = r0 + m.rlocal;
-        for (; r + (int64_t)m.rpp < r1; r += 2 * (int64_t)m.rpp) {
-          float d[2][8], o[2][8], v[2][8];
+    for (int k = 0; k < 8; ++k) { s[k] = 0.f; q[k] = 0.f; }
+    if (m.active && cg < m.cgs) {
+      float mean[8];
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int64_t off = (r + (int64_t)u * m.rpp) * C + coff;
-            load8<T>(dy + off, d[u]);
-            load8<T>(x + off, v[u]);
-            if constexpr (RELU) load8<T>(y + off, o[u]);
-          }
+      for (int k = 0; k < 8; ++k) mean[k] = saved[cg * 8 + k];
+      const int64_t coff = cg * 8;
+      int64_t r = r0 + m.rlocal;
+      for (; r + 3 * (int64_t)m.rpp < r1; r += 4 * (int64_t)m.rpp) {
+        float d[4][8], v[4][8];
+        unsigned bits[4];
 #pragma unroll
-          for (int u = 0; u < 2; ++u)
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              float dz = d[u][k];
-              if constexpr (RELU) dz = o[u][k] > 0.f ? dz : 0.f;
-              s[k] += dz;
-              q[k] += dz * (v[u][k] - mean[k]) * invstd[k];
-            }
+        for (int u = 0; u < 4; ++u) {
+          const int64_t row = r + (int64_t)u * m.rpp;
+          load8<T>(dy + row * C + coff, d[u]);
+          load8<T>(x + row * C + coff, v[u]);
+          if constexpr (RELU) bits[u] = mask[row * m.cgs + cg];
         }
-        for (; r < r1; r += m.rpp) {
-          float d[8], o[8], v[8];
-          const int64_t off = r * C + coff;
-          load8<T>(dy + off, d);
-          load8<T>(x + off, v);
-          if constexpr (RELU) load8<T>(y + off, o);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
-            float dz = d[k];
-            if constexpr (RELU) dz = o[k] > 0.f ? dz : 0.f;
+            float dz = d[u][k];
+            if constexpr (RELU) dz = (bits[u] >> k) & 1u ? dz : 0.f;
             s[k] += dz;
-            q[k] += dz * (v[k] - mean[k]) * invstd[k];
+            q[k] += dz * (v[u][k] - mean[k]);
           }
+      }
+      for (; r < r1; r += m.rpp) {
+        float d[8], v[8];
+        load8<T>(dy + r * C + coff, d);
+        load8<T>(x + r * C + coff, v);
+        unsigned bits = 0;
+        if constexpr (RELU) bits = mask[r * m.cgs + cg];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float dz = d[k];
+          if constexpr (RELU) dz = (bits >> k) & 1u ? dz : 0.f;
+          s[k] += dz;
+          q[k] += dz * (v[k] - mean[k]);
         }
       }
-      flush_partials(m, cg, s, q, sm, C);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) q[k] *= saved[C + cg * 8 + k];   // x invstd once per CTA, not per element
     }
+    cta_combine(m, cgb, s, q, sm, gsum, C);
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&gsum[i], sm[i]);
 }
 
 // ------------------------------------------------------------------ backward: apply
 // dx = gamma*invstd * (dz - mean(dz) - xhat * mean(dz*xhat)) ; dres = dz ; dgamma = sum dz*xhat ; dbeta = sum dz
 template <typename T, bool RELU, bool RES>
-__global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ y, const T* __restrict__ x,
-                                                                  const float* __restrict__ saved, const float* __restrict__ gsum,
-                                                                  const void* __restrict__ w, int wdt, T* __restrict__ dx, T* __restrict__ dres,
-                                                                  void* __restrict__ dw, void* __restrict__ db, int64_t M, int C) {
+__global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ mask,
+                                                                  const T* __restrict__ x, const float* __restrict__ saved,
+                                                                  const float* __restrict__ gsum, const void* __restrict__ w, int wdt,
+                                                                  T* __restrict__ dx, T* __restrict__ dres, void* __restrict__ dw,
+                                                                  void* __restrict__ db, int64_t M, int C) {
   const RowMap m = row_map(C);
   if (!m.active) return;
   const float inv_m = 1.f / (float)M;
   for (int cg = m.cg0; cg < m.cgs; cg += m.tpr) {
-    float mean[8], invstd[8], k1[8], k2[8], sc[8];
+    // dx = A*dz + B*x + D  with A = gamma*invstd, B = -A*invstd*mean(dz*xhat), D = -A*mean(dz) - B*mean
+    float ka[8], kb[8], kd[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int c = cg * 8 + k;
-      mean[k] = saved[c];
-      invstd[k] = saved[C + c];
+      const float mean = saved[c], invstd = saved[C + c];
       const float sdz = gsum[c], sdzx = gsum[C + c];
-      sc[k] = ld_w(w, wdt, c) * invstd[k];
-      k1[k] = sdz * inv_m;
-      k2[k] = sdzx * inv_m;
+      ka[k] = ld_w(w, wdt, c) * invstd;
+      kb[k] = -ka[k] * invstd * sdzx * inv_m;
+      kd[k] = -ka[k] * sdz * inv_m - kb[k] * mean;
       if (blockIdx.x == 0 && m.rlocal == 0) {
         st_w(dw, wdt, c, sdzx);
         st_w(db, wdt, c, sdz);
@@ -279,43 +304,43 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(const T* __res
     const int64_t stride = (int64_t)gridDim.x * m.rpp;
     const int64_t coff = cg * 8;
     int64_t r = (int64_t)blockIdx.x * m.rpp + m.rlocal;
-    for (; r + stride < M; r += 2 * stride) {
-      float d[2][8], o[2][8], v[2][8];
+    for (; r + 3 * stride < M; r += 4 * stride) {
+      float d[4][8], v[4][8];
+      unsigned bits[4];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int64_t off = (r + u * stride) * C + coff;
-        load8<T>(dy + off, d[u]);
-        load8<T>(x + off, v[u]);
-        if constexpr (RELU) load8<T>(y + off, o[u]);
+      for (int u = 0; u < 4; ++u) {
+        const int64_t row = r + u * stride;
+        load8<T>(dy + row * C + coff, d[u]);
+        load8<T>(x + row * C + coff, v[u]);
+        if constexpr (RELU) bits[u] = mask[row * m.cgs + cg];
       }
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < 4; ++u) {
         const int64_t off = (r + u * stride) * C + coff;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           float dz = d[u][k];
-          if constexpr (RELU) dz = o[u][k] > 0.f ? dz : 0.f;
+          if constexpr (RELU) dz = (bits[u] >> k) & 1u ? dz : 0.f;
           d[u][k] = dz;
-          const float xhat = (v[u][k] - mean[k]) * invstd[k];
-          v[u][k] = sc[k] * (dz - k1[k] - xhat * k2[k]);
+          v[u][k] = ka[k] * dz + kb[k] * v[u][k] + kd[k];
         }
         store8<T>(dx + off, v[u]);
         if constexpr (RES) store8<T>(dres + off, d[u]);
       }
     }
     for (; r < M; r += stride) {
-      float d[8], o[8], v[8];
+      float d[8], v[8];
       const int64_t off = r * C + coff;
       load8<T>(dy + off, d);
       load8<T>(x + off, v);
-      if constexpr (RELU) load8<T>(y + off, o);
+      unsigned bits = 0;
+      if constexpr (RELU) bits = mask[r * m.cgs + cg];
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         float dz = d[k];
-        if constexpr (RELU) dz = o[k] > 0.f ? dz : 0.f;
+        if constexpr (RELU) dz = (bits >> k) & 1u ? dz : 0.f;
         d[k] = dz;
-        const float xhat = (v[k] - mean[k]) * invstd[k];
-        v[k] = sc[k] * (dz - k1[k] - xhat * k2[k]);
+        v[k] = ka[k] * dz + kb[k] * v[k] + kd[k];
       }
       store8<T>(dx + off, v);
       if constexpr (RES) store8<T>(dres + off, d);
@@ -338,19 +363,24 @@ static void check_nhwc(const at::Tensor& t, const char* name) {
   TORCH_CHECK(t.is_contiguous(at::MemoryFormat::ChannelsLast), name, " must be channels_last contiguous");
 }
 
-struct Geometry { int64_t M; int C; int rpp; int sms; };
+struct Geometry { int64_t M; int C; int tpr; int rpp; int sms; size_t smem; };
 static Geometry geometry(const at::Tensor& x) {
   Geometry g;
   g.C = (int)x.size(1);
   g.M = x.numel() / g.C;
-  TORCH_CHECK(g.C % 8 == 0 && g.C <= 8192, "fused BN needs C % 8 == 0 and C <= 8192 (got ", g.C, ")");
-  const int tpr = std::min(g.C / 8, kBnThreads);
-  g.rpp = kBnThreads / tpr;
+  TORCH_CHECK(g.C % 8 == 0 && g.C <= 16384, "fused BN needs C % 8 == 0 and C <= 16384 (got ", g.C, ")");
+  g.tpr = std::min(g.C / 8, kBnThreads);
+  g.rpp = kBnThreads / g.tpr;
   g.sms = at::cuda::getCurrentDeviceProperties()->multiProcessorCount;
+  const bool pow2 = (g.tpr & (g.tpr - 1)) == 0;
+  const int slots = (pow2 && g.tpr < 32) ? kBnWarps : g.rpp;
+  g.smem = (size_t)slots * 2 * g.tpr * 8 * sizeof(float);
   return g;
 }
 static int reduce_grid(const Geometry& g, int* rows_per_block) {
-  int64_t blocks = (g.M + (int64_t)g.rpp * 16 - 1) / ((int64_t)g.rpp * 16);
+  // enough CTAs to fill the machine (>= 4 per SM when the tensor is big), but >= 32 row-passes per CTA so the
+  // combine/atomic tail stays small
+  int64_t blocks = (g.M + (int64_t)g.rpp * 32 - 1) / ((int64_t)g.rpp * 32);
   blocks = std::max<int64_t>(std::min<int64_t>(blocks, (int64_t)g.sms * 8), 1);
   int64_t rpb = (g.M + blocks - 1) / blocks;
   rpb = (rpb + g.rpp - 1) / g.rpp * g.rpp;
@@ -362,38 +392,42 @@ static int apply_grid(const Geometry& g) {
   return (int)std::max<int64_t>(std::min<int64_t>(blocks, (int64_t)g.sms * 8), 1);
 }
 
-// returns {y, saved(mean|invstd)} ; `work` = zeroed float[2C] accumulator supplied by the caller
 template <typename T>
-static void fwd_impl(const at::Tensor& x, const at::Tensor* res, at::Tensor& y, at::Tensor& work, at::Tensor& saved, const at::Tensor& w,
-                     const at::Tensor& b, at::Tensor& rm, at::Tensor& rv, bool training, float momentum, float eps, bool relu) {
+static void fwd_impl(const at::Tensor& x, const at::Tensor* res, at::Tensor& y, at::Tensor& mask, at::Tensor& work, at::Tensor& saved,
+                     const at::Tensor& w, const at::Tensor& b, at::Tensor& rm, at::Tensor& rv, at::Tensor& nbt, bool training, float momentum,
+                     float eps, bool relu) {
   const Geometry g = geometry(x);
   cudaStream_t st = at::cuda::getCurrentCUDAStream();
   const T* xp = reinterpret_cast<const T*>(x.data_ptr());
   T* yp = reinterpret_cast<T*>(y.data_ptr());
   const T* rp = res ? reinterpret_cast<const T*>(res->data_ptr()) : nullptr;
-  float* wk = work.data_ptr<float>();
+  float* wk = work.defined() ? work.data_ptr<float>() : nullptr;
   if (training) {
     int rpb;
     const int grid = reduce_grid(g, &rpb);
-    bn_stats_kernel<T><<<grid, kBnThreads, 2 * g.C * sizeof(float), st>>>(xp, wk, g.M, g.C, rpb);
+    bn_stats_kernel<T><<<grid, kBnThreads, g.smem, st>>>(xp, wk, g.M, g.C, rpb);
     C10_CUDA_KERNEL_LAUNCH_CHECK();
   }
   const int grid = apply_grid(g);
   float* rmp = rm.defined() ? rm.data_ptr<float>() : nullptr;
   float* rvp = rv.defined() ? rv.data_ptr<float>() : nullptr;
+  int64_t* nb = nbt.defined() ? nbt.data_ptr<int64_t>() : nullptr;
   float* sv = saved.defined() ? saved.data_ptr<float>() : nullptr;
+  uint8_t* mk = mask.defined() ? mask.data_ptr<uint8_t>() : nullptr;
   const int wdt = wdtype(w);
 #define APPLY(R, S) \
-  bn_apply_kernel<T, R, S><<<grid, kBnThreads, 0, st>>>(xp, rp, yp, wk, w.data_ptr(), b.data_ptr(), wdt, rmp, rvp, sv, g.M, g.C, eps, momentum, training ? 1 : 0)
+  bn_apply_kernel<T, R, S><<<grid, kBnThreads, 0, st>>>(xp, rp, yp, mk, wk, w.data_ptr(), b.data_ptr(), wdt, rmp, rvp, nb, sv, g.M, g.C, eps, momentum, training ? 1 : 0)
   if (relu) { if (res) APPLY(true, true); else APPLY(true, false); }
   else      { if (res) APPLY(false, true); else APPLY(false, false); }
 #undef APPLY
   C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
 
+// returns {y, saved(mean|invstd), relu_mask}; `work` = zeroed float[2C] accumulator supplied by the caller
 std::vector<at::Tensor> bn_act_forward(const at::Tensor& x, const c10::optional<at::Tensor>& residual, const at::Tensor& weight,
-                                       const at::Tensor& bias, at::Tensor running_mean, at::Tensor running_var, bool training, double momentum,
-                                       double eps, bool relu, at::Tensor work) {
+                                       const at::Tensor& bias, at::Tensor running_mean, at::Tensor running_var,
+                                       c10::optional<at::Tensor> num_batches_tracked, bool training, double momentum, double eps, bool relu,
+                                       bool need_mask, at::Tensor work) {
   check_nhwc(x, "x");
   TORCH_CHECK(weight.scalar_type() == bias.scalar_type() && weight.is_contiguous() && bias.is_contiguous());
   if (running_mean.defined()) TORCH_CHECK(running_mean.scalar_type() == at::kFloat && running_var.scalar_type() == at::kFloat, "running stats must be fp32");
@@ -407,56 +441,64 @@ std::vector<at::Tensor> bn_act_forward(const at::Tensor& x, const c10::optional<
   c10::cuda::CUDAGuard guard(x.device());
   const int C = (int)x.size(1);
   at::Tensor y = at::empty_like(x, x.options().memory_format(at::MemoryFormat::ChannelsLast));
-  at::Tensor saved;
+  at::Tensor saved, mask, nbt;
+  if (num_batches_tracked.has_value() && num_batches_tracked->defined()) {
+    nbt = *num_batches_tracked;
+    TORCH_CHECK(nbt.scalar_type() == at::kLong && nbt.is_cuda());
+  }
   if (training) {
     TORCH_CHECK(work.defined() && work.scalar_type() == at::kFloat && work.numel() >= 2 * C, "work buffer too small");
     saved = at::empty({2 * C}, x.options().dtype(at::kFloat));
-  } else {
-    work = running_mean;  // unused pointer
   }
+  if (relu && need_mask) mask = at::empty({x.numel() / 8}, x.options().dtype(at::kByte));
   switch (x.scalar_type()) {
-    case at::kBFloat16: fwd_impl<__nv_bfloat16>(x, res, y, work, saved, weight, bias, running_mean, running_var, training, (float)momentum, (float)eps, relu); break;
-    case at::kHalf: fwd_impl<__half>(x, res, y, work, saved, weight, bias, running_mean, running_var, training, (float)momentum, (float)eps, relu); break;
-    case at::kFloat: fwd_impl<float>(x, res, y, work, saved, weight, bias, running_mean, running_var, training, (float)momentum, (float)eps, relu); break;
+    case at::kBFloat16: fwd_impl<__nv_bfloat16>(x, res, y, mask, work, saved, weight, bias, running_mean, running_var, nbt, training, (float)momentum, (float)eps, relu); break;
+    case at::kHalf: fwd_impl<__half>(x, res, y, mask, work, saved, weight, bias, running_mean, running_var, nbt, training, (float)momentum, (float)eps, relu); break;
+    case at::kFloat: fwd_impl<float>(x, res, y, mask, work, saved, weight, bias, running_mean, running_var, nbt, training, (float)momentum, (float)eps, relu); break;
     default: TORCH_CHECK(false, "unsupported activation dtype");
   }
-  return {y, saved};
+  return {y, saved, mask};
 }
 
 template <typename T>
-static void bwd_impl(const at::Tensor& dy, const at::Tensor& y, const at::Tensor& x, const at::Tensor& saved, at::Tensor& work, const at::Tensor& w,
-                     at::Tensor& dx, at::Tensor& dres, at::Tensor& dw, at::Tensor& db, bool relu, bool has_res) {
+static void bwd_impl(const at::Tensor& dy, const at::Tensor& mask, const at::Tensor& x, const at::Tensor& saved, at::Tensor& work,
+                     const at::Tensor& w, at::Tensor& dx, at::Tensor& dres, at::Tensor& dw, at::Tensor& db, bool relu, bool write_res) {
   const Geometry g = geometry(x);
   cudaStream_t st = at::cuda::getCurrentCUDAStream();
   const T* dyp = reinterpret_cast<const T*>(dy.data_ptr());
-  const T* yp = relu ? reinterpret_cast<const T*>(y.data_ptr()) : nullptr;
+  const uint8_t* mk = relu ? mask.data_ptr<uint8_t>() : nullptr;
   const T* xp = reinterpret_cast<const T*>(x.data_ptr());
   float* wk = work.data_ptr<float>();
   const float* sv = saved.data_ptr<float>();
   int rpb;
   const int rgrid = reduce_grid(g, &rpb);
-  if (relu) bn_bwd_reduce_kernel<T, true><<<rgrid, kBnThreads, 2 * g.C * sizeof(float), st>>>(dyp, yp, xp, sv, wk, g.M, g.C, rpb);
-  else      bn_bwd_reduce_kernel<T, false><<<rgrid, kBnThreads, 2 * g.C * sizeof(float), st>>>(dyp, yp, xp, sv, wk, g.M, g.C, rpb);
+  if (relu) bn_bwd_reduce_kernel<T, true><<<rgrid, kBnThreads, g.smem, st>>>(dyp, mk, xp, sv, wk, g.M, g.C, rpb);
+  else      bn_bwd_reduce_kernel<T, false><<<rgrid, kBnThreads, g.smem, st>>>(dyp, mk, xp, sv, wk, g.M, g.C, rpb);
   C10_CUDA_KERNEL_LAUNCH_CHECK();
   const int grid = apply_grid(g);
   T* dxp = reinterpret_cast<T*>(dx.data_ptr());
-  T* drp = has_res ? reinterpret_cast<T*>(dres.data_ptr()) : nullptr;
+  T* drp = write_res ? reinterpret_cast<T*>(dres.data_ptr()) : nullptr;
   const int wdt = wdtype(w);
 #define BAPPLY(R, S) \
-  bn_bwd_apply_kernel<T, R, S><<<grid, kBnThreads, 0, st>>>(dyp, yp, xp, sv, wk, w.data_ptr(), wdt, dxp, drp, dw.data_ptr(), db.data_ptr(), g.M, g.C)
-  if (relu) { if (has_res) BAPPLY(true, true); else BAPPLY(true, false); }
-  else      { if (has_res) BAPPLY(false, true); else BAPPLY(false, false); }
+  bn_bwd_apply_kernel<T, R, S><<<grid, kBnThreads, 0, st>>>(dyp, mk, xp, sv, wk, w.data_ptr(), wdt, dxp, drp, dw.data_ptr(), db.data_ptr(), g.M, g.C)
+  if (relu) { if (write_res) BAPPLY(true, true); else BAPPLY(true, false); }
+  else      { if (write_res) BAPPLY(false, true); else BAPPLY(false, false); }
 #undef BAPPLY
   C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
 
 // returns {dx, dres (undefined if !has_residual), dweight, dbias}
-std::vector<at::Tensor> bn_act_backward(const at::Tensor& dy_in, const at::Tensor& x, const at::Tensor& y, const at::Tensor& weight,
-                                        const at::Tensor& saved, bool relu, bool has_residual, at::Tensor work) {
+std::vector<at::Tensor> bn_act_backward(const at::Tensor& dy_in, const at::Tensor& x, const c10::optional<at::Tensor>& mask_opt,
+                                        const at::Tensor& weight, const at::Tensor& saved, bool relu, bool has_residual, at::Tensor work) {
   check_nhwc(x, "x");
   at::Tensor dy = dy_in.is_contiguous(at::MemoryFormat::ChannelsLast) ? dy_in : dy_in.contiguous(at::MemoryFormat::ChannelsLast);
   TORCH_CHECK(dy.scalar_type() == x.scalar_type() && dy.sizes() == x.sizes());
-  if (relu) check_nhwc(y, "y");
+  at::Tensor mask;
+  if (relu) {
+    TORCH_CHECK(mask_opt.has_value() && mask_opt->defined() && mask_opt->scalar_type() == at::kByte && mask_opt->numel() == x.numel() / 8,
+                "ReLU backward needs the forward's bit mask");
+    mask = *mask_opt;
+  }
   const int C = (int)x.size(1);
   TORCH_CHECK(work.defined() && work.scalar_type() == at::kFloat && work.numel() >= 2 * C, "work buffer too small");
   c10::cuda::CUDAGuard guard(x.device());
@@ -466,12 +508,307 @@ std::vector<at::Tensor> bn_act_backward(const at::Tensor& dy_in, const at::Tenso
   at::Tensor dw = at::empty_like(weight), db = at::empty_like(weight);
   const bool write_res = has_residual && relu;  // without ReLU the residual gradient IS dy: no copy
   switch (x.scalar_type()) {
-    case at::kBFloat16: bwd_impl<__nv_bfloat16>(dy, y, x, saved, work, weight, dx, dres, dw, db, relu, write_res); break;
-    case at::kHalf: bwd_impl<__half>(dy, y, x, saved, work, weight, dx, dres, dw, db, relu, write_res); break;
-    case at::kFloat: bwd_impl<float>(dy, y, x, saved, work, weight, dx, dres, dw, db, relu, write_res); break;
+    case at::kBFloat16: bwd_impl<__nv_bfloat16>(dy, mask, x, saved, work, weight, dx, dres, dw, db, relu, write_res); break;
+    case at::kHalf: bwd_impl<__half>(dy, mask, x, saved, work, weight, dx, dres, dw, db, relu, write_res); break;
+    case at::kFloat: bwd_impl<float>(dy, mask, x, saved, work, weight, dx, dres, dw, db, relu, write_res); break;
     default: TORCH_CHECK(false, "unsupported activation dtype");
   }
   return {dx, dres, dw, db};
+}
+
+}  // namespace ptd
+
+// ====================================================================================================================
+// Fused ResNet stem: BatchNorm + ReLU + MaxPool(3x3, stride 2, pad 1), NHWC.
+//
+// torchvision's stem (/root/reference/distributed.py:136-139 -> resnet.conv1/bn1/relu/maxpool) writes the full
+// 112x112 activation, re-reads it for the pool, and in backward runs ATen's max_pool_backward_nhwc with int64 indices
+// (1.7 ms / step on B200, see profiles/).  Here the normalised activation never touches HBM:
+//   forward : one pass over the conv output: BN -> ReLU -> 3x3 max -> pooled output + a 4-bit arg-max code per element
+//             (code 15 = "all candidates <= 0": the ReLU killed the gradient)
+//   backward: two passes over the INPUT domain; each input position gathers the (at most 4) pooled gradients whose
+//             window selected it, which yields dz for the BN backward reductions / apply without ever materialising
+//             the 112x112 gradient of the pool.
+namespace ptd {
+
+struct PoolGeom { int H, W, OH, OW; };
+
+__device__ __forceinline__ void stem_scale_shift(const float* gsum, const float* rm, const float* rv, const void* w, const void* b, int wdt,
+                                                 int cg, int C, float inv_m, float eps, int training, float (&sc)[8], float (&sh)[8],
+                                                 float (&mean)[8], float (&var)[8]) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = cg * 8 + k;
+    if (training) {
+      mean[k] = gsum[c] * inv_m;
+      var[k] = fmaxf(gsum[C + c] * inv_m - mean[k] * mean[k], 0.f);
+    } else {
+      mean[k] = rm[c];
+      var[k] = rv[c];
+    }
+    const float invstd = rsqrtf(var[k] + eps);
+    sc[k] = ld_w(w, wdt, c) * invstd;
+    sh[k] = ld_w(b, wdt, c) - mean[k] * sc[k];
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kBnThreads) stem_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, uint32_t* __restrict__ code,
+                                                              const float* __restrict__ gsum, const void* __restrict__ w,
+                                                              const void* __restrict__ b, int wdt, float* __restrict__ running_mean,
+                                                              float* __restrict__ running_var, int64_t* __restrict__ nbt,
+                                                              float* __restrict__ saved, int64_t M, int N, int C, PoolGeom g, float eps,
+                                                              float momentum, int training) {
+  const int cgs = C >> 3;
+  const int cg = threadIdx.x % cgs;                 // host guarantees blockDim.x % cgs == 0
+  float sc[8], sh[8], mean[8], var[8];
+  stem_scale_shift(gsum, running_mean, running_var, w, b, wdt, cg, C, 1.f / (float)M, eps, training, sc, sh, mean, var);
+  if (training && blockIdx.x == 0 && threadIdx.x < cgs) {
+    if (threadIdx.x == 0 && nbt) *nbt += 1;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = cg * 8 + k;
+      saved[c] = mean[k];
+      saved[C + c] = rsqrtf(var[k] + eps);
+      if (running_mean) {
+        const float unbiased = M > 1 ? var[k] * ((float)M / (float)(M - 1)) : var[k];
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean[k];
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+      }
+    }
+  }
+  const int64_t total = (int64_t)N * g.OH * g.OW;
+  const int ppb = blockDim.x / cgs;                  // output pixels per CTA pass
+  for (int64_t p = (int64_t)blockIdx.x * ppb + threadIdx.x / cgs; p < total; p += (int64_t)gridDim.x * ppb) {
+    const int ow = (int)(p % g.OW);
+    const int oh = (int)((p / g.OW) % g.OH);
+    const int64_t n = p / ((int64_t)g.OW * g.OH);
+    float best[8];
+    uint32_t sel[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { best[k] = 0.f; sel[k] = 15u; }
+    const T* base = x + n * g.H * g.W * C + cg * 8;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int ih = 2 * oh - 1 + kh;
+      if (ih < 0 || ih >= g.H) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int iw = 2 * ow - 1 + kw;
+        if (iw < 0 || iw >= g.W) continue;
+        float f[8];
+        load8<T>(base + ((int64_t)ih * g.W + iw) * C, f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float v = f[k] * sc[k] + sh[k];
+          if (v > best[k]) { best[k] = v; sel[k] = (uint32_t)(kh * 3 + kw); }
+        }
+      }
+    }
+    store8<T>(y + p * C + cg * 8, best);
+    if (code) {
+      uint32_t word = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) word |= sel[k] << (4 * k);
+      code[p * cgs + cg] = word;
+    }
+  }
+}
+
+// dz (gradient w.r.t. the BN+ReLU output at one input position) = sum of the pooled gradients that selected it
+template <typename T>
+__device__ __forceinline__ void stem_gather_dz(const T* __restrict__ dp, const uint32_t* __restrict__ code, int64_t n, int ih, int iw, int cg,
+                                               int cgs, int C, const PoolGeom& g, float (&dz)[8]) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) dz[k] = 0.f;
+  const int oh0 = ih >> 1, oh1 = min((ih + 1) >> 1, g.OH - 1);
+  const int ow0 = iw >> 1, ow1 = min((iw + 1) >> 1, g.OW - 1);
+  for (int oh = oh0; oh <= oh1; ++oh) {
+    const int kh = ih - (2 * oh - 1);
+    for (int ow = ow0; ow <= ow1; ++ow) {
+      const int kw = iw - (2 * ow - 1);
+      const uint32_t want = (uint32_t)(kh * 3 + kw);
+      const int64_t p = (n * g.OH + oh) * g.OW + ow;
+      const uint32_t word = code[p * cgs + cg];
+      float d[8];
+      load8<T>(dp + p * C + cg * 8, d);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) dz[k] += ((word >> (4 * k)) & 15u) == want ? d[k] : 0.f;
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kBnThreads) stem_bwd_reduce_kernel(const T* __restrict__ dp, const uint32_t* __restrict__ code,
+                                                                     const T* __restrict__ x, const float* __restrict__ saved,
+                                                                     float* __restrict__ gsum, int64_t M, int C, PoolGeom g,
+                                                                     int rows_per_block) {
+  extern __shared__ float sm[];
+  const RowMap m = row_map(C);
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = min(M, r0 + (int64_t)rows_per_block);
+  for (int cgb = 0; cgb < m.cgs; cgb += m.tpr) {
+    const int cg = cgb + m.cg0;
+    float s[8], q[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { s[k] = 0.f; q[k] = 0.f; }
+    if (m.active && cg < m.cgs) {
+      float mean[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) mean[k] = saved[cg * 8 + k];
+      for (int64_t r = r0 + m.rlocal; r < r1; r += m.rpp) {
+        const int iw = (int)(r % g.W), ih = (int)((r / g.W) % g.H);
+        const int64_t n = r / ((int64_t)g.W * g.H);
+        float dz[8], v[8];
+        stem_gather_dz<T>(dp, code, n, ih, iw, cg, m.cgs, C, g, dz);
+        load8<T>(x + r * C + cg * 8, v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { s[k] += dz[k]; q[k] += dz[k] * (v[k] - mean[k]); }
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) q[k] *= saved[C + cg * 8 + k];
+    }
+    cta_combine(m, cgb, s, q, sm, gsum, C);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kBnThreads) stem_bwd_apply_kernel(const T* __restrict__ dp, const uint32_t* __restrict__ code,
+                                                                    const T* __restrict__ x, const float* __restrict__ saved,
+                                                                    const float* __restrict__ gsum, const void* __restrict__ w, int wdt,
+                                                                    T* __restrict__ dx, void* __restrict__ dw, void* __restrict__ db,
+                                                                    int64_t M, int C, PoolGeom g) {
+  const RowMap m = row_map(C);
+  if (!m.active) return;
+  const float inv_m = 1.f / (float)M;
+  for (int cg = m.cg0; cg < m.cgs; cg += m.tpr) {
+    float ka[8], kb[8], kd[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = cg * 8 + k;
+      const float mean = saved[c], invstd = saved[C + c];
+      const float sdz = gsum[c], sdzx = gsum[C + c];
+      ka[k] = ld_w(w, wdt, c) * invstd;
+      kb[k] = -ka[k] * invstd * sdzx * inv_m;
+      kd[k] = -ka[k] * sdz * inv_m - kb[k] * mean;
+      if (blockIdx.x == 0 && m.rlocal == 0) {
+        st_w(dw, wdt, c, sdzx);
+        st_w(db, wdt, c, sdz);
+      }
+    }
+    const int64_t stride = (int64_t)gridDim.x * m.rpp;
+    for (int64_t r = (int64_t)blockIdx.x * m.rpp + m.rlocal; r < M; r += stride) {
+      const int iw = (int)(r % g.W), ih = (int)((r / g.W) % g.H);
+      const int64_t n = r / ((int64_t)g.W * g.H);
+      float dz[8], v[8];
+      stem_gather_dz<T>(dp, code, n, ih, iw, cg, m.cgs, C, g, dz);
+      load8<T>(x + r * C + cg * 8, v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = ka[k] * dz[k] + kb[k] * v[k] + kd[k];
+      store8<T>(dx + r * C + cg * 8, v);
+    }
+  }
+}
+
+static PoolGeom pool_geom(const at::Tensor& x) {
+  PoolGeom g;
+  g.H = (int)x.size(2);
+  g.W = (int)x.size(3);
+  g.OH = (g.H + 2 - 3) / 2 + 1;
+  g.OW = (g.W + 2 - 3) / 2 + 1;
+  return g;
+}
+
+template <typename T>
+static void stem_fwd_impl(const at::Tensor& x, at::Tensor& y, at::Tensor& code, at::Tensor& work, at::Tensor& saved, const at::Tensor& w,
+                          const at::Tensor& b, at::Tensor& rm, at::Tensor& rv, at::Tensor& nbt, bool training, float momentum, float eps) {
+  const Geometry g = geometry(x);
+  const PoolGeom pg = pool_geom(x);
+  cudaStream_t st = at::cuda::getCurrentCUDAStream();
+  const T* xp = reinterpret_cast<const T*>(x.data_ptr());
+  float* wk = work.defined() ? work.data_ptr<float>() : nullptr;
+  if (training) {
+    int rpb;
+    const int grid = reduce_grid(g, &rpb);
+    bn_stats_kernel<T><<<grid, kBnThreads, g.smem, st>>>(xp, wk, g.M, g.C, rpb);
+    C10_CUDA_KERNEL_LAUNCH_CHECK();
+  }
+  const int cgs = g.C / 8;
+  const int64_t total = x.size(0) * pg.OH * pg.OW;
+  const int ppb = kBnThreads / cgs;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((total + ppb - 1) / ppb, (int64_t)g.sms * 16));
+  stem_fwd_kernel<T><<<grid, kBnThreads, 0, st>>>(xp, reinterpret_cast<T*>(y.data_ptr()),
+                                                 code.defined() ? reinterpret_cast<uint32_t*>(code.data_ptr()) : nullptr, wk, w.data_ptr(),
+                                                 b.data_ptr(), wdtype(w), rm.defined() ? rm.data_ptr<float>() : nullptr,
+                                                 rv.defined() ? rv.data_ptr<float>() : nullptr, nbt.defined() ? nbt.data_ptr<int64_t>() : nullptr,
+                                                 saved.defined() ? saved.data_ptr<float>() : nullptr, g.M, (int)x.size(0), g.C, pg, eps, momentum,
+                                                 training ? 1 : 0);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+// relu(bn(x)) -> maxpool 3x3/2/1.  returns {y_pool, saved, code}
+std::vector<at::Tensor> stem_forward(const at::Tensor& x, const at::Tensor& weight, const at::Tensor& bias, at::Tensor running_mean,
+                                     at::Tensor running_var, c10::optional<at::Tensor> num_batches_tracked, bool training, double momentum,
+                                     double eps, bool need_code, at::Tensor work) {
+  check_nhwc(x, "x");
+  const int C = (int)x.size(1);
+  TORCH_CHECK(C % 8 == 0 && kBnThreads % (C / 8) == 0, "fused stem needs C/8 to divide ", kBnThreads);
+  TORCH_CHECK(training || running_mean.defined(), "eval mode needs running statistics");
+  c10::cuda::CUDAGuard guard(x.device());
+  const PoolGeom pg = pool_geom(x);
+  at::Tensor y = at::empty({x.size(0), C, pg.OH, pg.OW}, x.options().memory_format(at::MemoryFormat::ChannelsLast));
+  at::Tensor saved, code, nbt;
+  if (num_batches_tracked.has_value() && num_batches_tracked->defined()) nbt = *num_batches_tracked;
+  if (training) {
+    TORCH_CHECK(work.defined() && work.numel() >= 2 * C, "work buffer too small");
+    saved = at::empty({2 * C}, x.options().dtype(at::kFloat));
+  }
+  if (need_code) code = at::empty({y.numel() / 8}, x.options().dtype(at::kInt));
+  switch (x.scalar_type()) {
+    case at::kBFloat16: stem_fwd_impl<__nv_bfloat16>(x, y, code, work, saved, weight, bias, running_mean, running_var, nbt, training, (float)momentum, (float)eps); break;
+    case at::kHalf: stem_fwd_impl<__half>(x, y, code, work, saved, weight, bias, running_mean, running_var, nbt, training, (float)momentum, (float)eps); break;
+    case at::kFloat: stem_fwd_impl<float>(x, y, code, work, saved, weight, bias, running_mean, running_var, nbt, training, (float)momentum, (float)eps); break;
+    default: TORCH_CHECK(false, "unsupported activation dtype");
+  }
+  return {y, saved, code};
+}
+
+template <typename T>
+static void stem_bwd_impl(const at::Tensor& dp, const at::Tensor& code, const at::Tensor& x, const at::Tensor& saved, at::Tensor& work,
+                          const at::Tensor& w, at::Tensor& dx, at::Tensor& dw, at::Tensor& db) {
+  const Geometry g = geometry(x);
+  const PoolGeom pg = pool_geom(x);
+  cudaStream_t st = at::cuda::getCurrentCUDAStream();
+  const T* dpp = reinterpret_cast<const T*>(dp.data_ptr());
+  const uint32_t* cp = reinterpret_cast<const uint32_t*>(code.data_ptr());
+  const T* xp = reinterpret_cast<const T*>(x.data_ptr());
+  int rpb;
+  const int rgrid = reduce_grid(g, &rpb);
+  stem_bwd_reduce_kernel<T><<<rgrid, kBnThreads, g.smem, st>>>(dpp, cp, xp, saved.data_ptr<float>(), work.data_ptr<float>(), g.M, g.C, pg, rpb);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((g.M + g.rpp - 1) / g.rpp, (int64_t)g.sms * 16));
+  stem_bwd_apply_kernel<T><<<grid, kBnThreads, 0, st>>>(dpp, cp, xp, saved.data_ptr<float>(), work.data_ptr<float>(), w.data_ptr(), wdtype(w),
+                                                       reinterpret_cast<T*>(dx.data_ptr()), dw.data_ptr(), db.data_ptr(), g.M, g.C, pg);
+  C10_CUDA_KERNEL_LAUNCH_CHECK();
+}
+
+// returns {dx, dweight, dbias}
+std::vector<at::Tensor> stem_backward(const at::Tensor& dp_in, const at::Tensor& x, const at::Tensor& code, const at::Tensor& weight,
+                                      const at::Tensor& saved, at::Tensor work) {
+  check_nhwc(x, "x");
+  at::Tensor dp = dp_in.is_contiguous(at::MemoryFormat::ChannelsLast) ? dp_in : dp_in.contiguous(at::MemoryFormat::ChannelsLast);
+  const int C = (int)x.size(1);
+  TORCH_CHECK(dp.scalar_type() == x.scalar_type() && dp.size(1) == C && code.scalar_type() == at::kInt && code.numel() == dp.numel() / 8);
+  TORCH_CHECK(work.defined() && work.numel() >= 2 * C, "work buffer too small");
+  c10::cuda::CUDAGuard guard(x.device());
+  at::Tensor dx = at::empty_like(x, x.options().memory_format(at::MemoryFormat::ChannelsLast));
+  at::Tensor dw = at::empty_like(weight), db = at::empty_like(weight);
+  switch (x.scalar_type()) {
+    case at::kBFloat16: stem_bwd_impl<__nv_bfloat16>(dp, code, x, saved, work, weight, dx, dw, db); break;
+    case at::kHalf: stem_bwd_impl<__half>(dp, code, x, saved, work, weight, dx, dw, db); break;
+    case at::kFloat: stem_bwd_impl<float>(dp, code, x, saved, work, weight, dx, dw, db); break;
+    default: TORCH_CHECK(false, "unsupported activation dtype");
+  }
+  return {dx, dw, db};
 }
 
 }  // namespace ptd

@@ -40,10 +40,17 @@ void amp_update_scale(at::Tensor scale, at::Tensor growth_tracker, at::Tensor fo
 
 // ---- bn_act.cu
 std::vector<at::Tensor> bn_act_forward(const at::Tensor& x, const c10::optional<at::Tensor>& residual, const at::Tensor& weight,
-                                       const at::Tensor& bias, at::Tensor running_mean, at::Tensor running_var, bool training,
-                                       double momentum, double eps, bool relu, at::Tensor work);
-std::vector<at::Tensor> bn_act_backward(const at::Tensor& dy, const at::Tensor& x, const at::Tensor& y, const at::Tensor& weight,
-                                        const at::Tensor& saved, bool relu, bool has_residual, at::Tensor work);
+                                       const at::Tensor& bias, at::Tensor running_mean, at::Tensor running_var,
+                                       c10::optional<at::Tensor> num_batches_tracked, bool training, double momentum, double eps, bool relu,
+                                       bool need_mask, at::Tensor work);
+std::vector<at::Tensor> bn_act_backward(const at::Tensor& dy, const at::Tensor& x, const c10::optional<at::Tensor>& mask,
+                                        const at::Tensor& weight, const at::Tensor& saved, bool relu, bool has_residual, at::Tensor work);
+
+std::vector<at::Tensor> stem_forward(const at::Tensor& x, const at::Tensor& weight, const at::Tensor& bias, at::Tensor running_mean,
+                                     at::Tensor running_var, c10::optional<at::Tensor> num_batches_tracked, bool training, double momentum,
+                                     double eps, bool need_code, at::Tensor work);
+std::vector<at::Tensor> stem_backward(const at::Tensor& dp, const at::Tensor& x, const at::Tensor& code, const at::Tensor& weight,
+                                      const at::Tensor& saved, at::Tensor work);
 
 // ---- data_ops.cu
 at::Tensor normalize_nhwc(const at::Tensor& src, const at::Tensor& mean, const at::Tensor& std, int64_t out_dtype, bool channels_last);

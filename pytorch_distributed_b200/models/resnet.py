@@ -15,6 +15,7 @@ import torch
 import torch.nn as nn
 
 from ..ops.bn_act import begin_step, bn_act
+from ..ops.stem import bn_relu_maxpool
 
 
 class BNAct(nn.BatchNorm2d):
@@ -26,11 +27,11 @@ class BNAct(nn.BatchNorm2d):
         self.fused = fused
 
     def forward(self, x, residual=None):  # type: ignore[override]
-        if self.training and self.track_running_stats and self.num_batches_tracked is not None:
-            self.num_batches_tracked.add_(1)
-        return bn_act(x, self.weight, self.bias, self.running_mean, self.running_var,
-                      residual=residual, relu=self.relu, training=self.training or not self.track_running_stats,
-                      momentum=0.1 if self.momentum is None else self.momentum, eps=self.eps, fused=self.fused)
+        training = self.training or not self.track_running_stats
+        nbt = self.num_batches_tracked if (self.training and self.track_running_stats) else None   # bumped inside the kernel
+        return bn_act(x, self.weight, self.bias, self.running_mean, self.running_var, residual=residual, relu=self.relu,
+                      training=training, momentum=0.1 if self.momentum is None else self.momentum, eps=self.eps, fused=self.fused,
+                      num_batches_tracked=nbt)
 
 
 def _conv3x3(cin, cout, stride=1, groups=1, dilation=1):
@@ -134,7 +135,11 @@ class ResNet(nn.Module):
     def forward(self, x):
         if self.training:
             begin_step(x.device)      # recycle the BN accumulator workspace: one memset per step
-        x = self.maxpool(self.bn1(self.conv1(x)))
+        bn = self.bn1
+        nbt = bn.num_batches_tracked if (bn.training and bn.track_running_stats) else None
+        x = bn_relu_maxpool(self.conv1(x), bn.weight, bn.bias, bn.running_mean, bn.running_var,   # fused stem tail
+                            training=bn.training or not bn.track_running_stats, momentum=0.1 if bn.momentum is None else bn.momentum,
+                            eps=bn.eps, fused=bn.fused, num_batches_tracked=nbt)
         x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
         return self.fc(torch.flatten(self.avgpool(x), 1))
 

@@ -68,37 +68,41 @@ def begin_step(device) -> None:
 
 class _BnActFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, residual, weight, bias, running_mean, running_var, training, momentum, eps, relu):
+    def forward(ctx, x, residual, weight, bias, running_mean, running_var, nbt, training, momentum, eps, relu):
         from .. import _ext
         C = _ext.lib()
         nc = x.size(1)
         ws = workspace(x.device)
+        need_grad = any(ctx.needs_input_grad[:4])
         if training:
             work, gen = ws.take(4 * nc)
         else:
             work, gen = torch.empty(0, dtype=torch.float32, device=x.device), -1
         _ext.note_launch(2 if training else 1)
-        y, saved = C.bn_act_forward(x, residual, weight, bias, running_mean, running_var, training, momentum, eps, relu,
-                                    work[: 2 * nc] if training else work)
+        y, saved, mask = C.bn_act_forward(x, residual, weight, bias, running_mean, running_var, nbt, training, momentum, eps, relu,
+                                          need_grad, work[: 2 * nc] if training else work)
         ctx.relu = relu
         ctx.has_res = residual is not None
         ctx.work = work[2 * nc:] if training else None
         ctx.gen = gen
         ctx.ws = ws
-        ctx.save_for_backward(x, y if relu else None, weight, saved)
+        if need_grad:
+            if not training:
+                raise RuntimeError("fused bn_act: backward through eval-mode batch norm is not supported")
+            ctx.save_for_backward(x, mask if relu else None, weight, saved)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         from .. import _ext
         C = _ext.lib()
-        x, y, weight, saved = ctx.saved_tensors
+        x, mask, weight, saved = ctx.saved_tensors
         work = ctx.work
         if work is None or (ctx.gen != -1 and ctx.gen != ctx.ws.generation):
             work = torch.zeros(2 * x.size(1), dtype=torch.float32, device=x.device)   # slice was recycled: use a fresh one
         _ext.note_launch(2)
-        dx, dres, dw, db = C.bn_act_backward(dy, x, y if y is not None else x, weight, saved, ctx.relu, ctx.has_res, work)
-        return dx, (dres if ctx.has_res else None), dw, db, None, None, None, None, None, None
+        dx, dres, dw, db = C.bn_act_backward(dy, x, mask, weight, saved, ctx.relu, ctx.has_res, work)
+        return dx, (dres if ctx.has_res else None), dw, db, None, None, None, None, None, None, None
 
 
 def _can_fuse(x, weight, residual, running_mean=True) -> bool:
@@ -110,14 +114,18 @@ def _can_fuse(x, weight, residual, running_mean=True) -> bool:
 
 
 def bn_act(x, weight, bias, running_mean, running_var, residual: Optional[torch.Tensor] = None, relu: bool = True,
-           training: bool = True, momentum: float = 0.1, eps: float = 1e-5, fused: Optional[bool] = None):
+           training: bool = True, momentum: float = 0.1, eps: float = 1e-5, fused: Optional[bool] = None,
+           num_batches_tracked: Optional[torch.Tensor] = None):
     """relu(batch_norm(x) + residual).  ``fused=None`` picks the CUDA kernels whenever the layout allows it."""
     ok = _can_fuse(x, weight, residual, running_mean)
     use = ok if fused is None else (fused and ok)
     if not use:
         if weight is not None and x.is_cuda and weight.dtype != torch.float32 and x.dtype != weight.dtype:
             weight, bias = weight.to(x.dtype), bias.to(x.dtype)
+        if training and num_batches_tracked is not None:
+            num_batches_tracked.add_(1)
         return bn_act_reference(x, weight, bias, running_mean, running_var, residual, relu, training, momentum, eps)
     if not training and running_mean is None:
         raise ValueError("eval mode needs running statistics")
-    return _BnActFn.apply(x, residual, weight, bias, running_mean, running_var, training, float(momentum), float(eps), relu)
+    return _BnActFn.apply(x, residual, weight, bias, running_mean, running_var, num_batches_tracked, training, float(momentum),
+                          float(eps), relu)

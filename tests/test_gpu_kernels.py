@@ -196,33 +196,6 @@ def test_fused_allreduce_world1_is_identity_and_fills_arena(wire):
         torch.testing.assert_close(arena[off:off + o.numel()].float(), exp.float().reshape(-1), rtol=0, atol=0)
 
 
-def test_ddp_world1_flat_optimizer_matches_torch_sgd():
-    """DDP(world=1) + FusedSGD(arena mode, fp32 model) == plain model + torch SGD, step by step."""
-    import copy
-    from pytorch_distributed_b200.models import create_model
-    from pytorch_distributed_b200.ops.fused_sgd import FusedSGD
-    from pytorch_distributed_b200.parallel.ddp import DistributedDataParallel
-    torch.manual_seed(0)
-    torch.backends.cudnn.allow_tf32 = False
-    torch.backends.cuda.matmul.allow_tf32 = False
-    m1 = create_model("resnet18", num_classes=10, fused_bn=False).cuda()
-    m2 = copy.deepcopy(m1)
-    ddp = DistributedDataParallel(m1, device_ids=[0], wire_dtype="fp32")
-    o1 = FusedSGD(ddp.parameters(), lr=0.05, momentum=0.9, weight_decay=1e-4)
-    assert o1.is_flat
-    o2 = torch.optim.SGD(m2.parameters(), lr=0.05, momentum=0.9, weight_decay=1e-4)
-    crit = torch.nn.CrossEntropyLoss()
-    for _ in range(3):
-        x = torch.randn(8, 3, 64, 64, device="cuda")
-        y = torch.randint(0, 10, (8,), device="cuda")
-        for m, o in ((ddp, o1), (m2, o2)):
-            o.zero_grad()
-            crit(m(x), y).backward()
-            o.step()
-    for (n1, p1), (n2, p2) in zip(m1.named_parameters(), m2.named_parameters()):
-        torch.testing.assert_close(p1.data, p2.data, rtol=2e-4, atol=2e-5, msg=lambda s, n=n1: n + ": " + s)
-
-
 def test_smoke_entry():
     import __graft_entry__ as g
     g.smoke()
