@@ -46,6 +46,7 @@ def parse():
     p.add_argument("--no-fused-bn", action="store_true")
     p.add_argument("--optimizer", default="fused")
     p.add_argument("--skip-e2e", action="store_true")
+    p.add_argument("--no-cuda-graph", action="store_true")
     p.add_argument("--entry", default="distributed", choices=["distributed", "apex_distributed", "horovod_distributed"])
     p.add_argument("--opt-level", default="O2")
     return p.parse_args()
@@ -155,14 +156,8 @@ def run_own(a):
     losses, top1, top5 = AverageMeter("Loss"), AverageMeter("Acc@1"), AverageMeter("Acc@5")
     metrics = driver.MetricPipeline(getattr(st, "comm", None), device, (losses, top1, top5), reduce=True)
 
-    def step(images, target):
-        output = st.forward(model, images)
-        loss = criterion(output.float() if output.dtype != torch.float32 else output, target)
-        metrics.push(output, target, loss, images.size(0))
-        optimizer.zero_grad()
-        st.backward(loss, optimizer)
-        optimizer.step()
-        metrics.poll()
+    use_graph = (not a.no_cuda_graph) and st.graph_capable
+    step = driver.TrainStep(st, model, criterion, optimizer, metrics, use_graph=use_graph, warmup=2)   # captured inside warm-up
 
     model.train()
     # ---------------- phase A: device-resident inputs (the `value`)
@@ -236,7 +231,7 @@ def run_own(a):
             "config": {"model": a.arch, "global_batch": B * world, "seq_len": None, "image_size": args.image_size,
                        "parallelism": "dp%d" % world, "entry": a.entry, "comm": getattr(comm, "backend", "none"),
                        "nvls": bool(getattr(comm, "nvls", False)), "channels_last": bool(args.channels_last),
-                       "fused_bn": args.fused_bn is not False, "optimizer": a.optimizer,
+                       "fused_bn": args.fused_bn is not False, "optimizer": a.optimizer, "cuda_graph": step.graph is not None,
                        "l2_policy": "inputs larger than L2 (4 x 38.5 MB bf16 batches + GBs of activations per step)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "impl": "own", "host_enqueue_ms_per_step": host_ms,
             "final_loss": losses.val,

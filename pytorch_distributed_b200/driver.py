@@ -87,11 +87,12 @@ class MetricPipeline:
                 out[0], out[1], out[2] = loss.detach().float(), a1[0], a5[0]
             self._apply(out.tolist(), n)
             return
-        if len(self.pending) >= len(self.ring) - 1:
-            self.poll(block_oldest=True)
-        i = self.slot
-        self.slot = (self.slot + 1) % len(self.ring)
-        dev = self.dev[i]
+        dev = self.dev[self.slot]
+        self.launch(output, target, loss, dev)
+        self.fetch(dev, n)
+
+    def launch(self, output, target, loss, dev) -> None:
+        """Enqueue the metric kernel writing into ``dev`` (capturable in a CUDA graph)."""
         lossf = loss.detach()
         if lossf.dtype != torch.float32:
             lossf = lossf.float()
@@ -99,10 +100,16 @@ class MetricPipeline:
             self.comm.metrics(output.detach(), target, lossf, dev)
         else:
             from . import _ext
-            C = _ext.lib()
-            _local_metrics(C, output.detach(), target, lossf, dev)
+            _local_metrics(_ext.lib(), output.detach(), target, lossf, dev)
             if self.reduce and self.comm.world > 1:
                 self.comm.reduce_scalars_(dev[:3], average=True)
+
+    def fetch(self, dev, n: int) -> None:
+        """16-byte D2H copy of a finished (or enqueued) metric vector into the pinned ring + completion event."""
+        if len(self.pending) >= len(self.ring) - 1:
+            self.poll(block_oldest=True)
+        i = self.slot
+        self.slot = (self.slot + 1) % len(self.ring)
         self.ring[i].copy_(dev, non_blocking=True)
         self.d2h_bytes += 16
         ev = torch.cuda.Event()
@@ -146,6 +153,64 @@ def _local_metrics(C, output, target, loss, out):
     a.launch_metrics(0, output, target, loss, out)
 
 
+# ====================================================================== one optimisation step (eager or CUDA graph)
+class TrainStep:
+    """forward + loss + metric kernel + backward (fused bucket all-reduce on the side stream) + optimizer.
+
+    With ``use_graph`` the whole step - several hundred kernels on two streams - is captured into ONE CUDA graph after
+    ``warmup`` eager iterations and replayed afterwards: the host then enqueues a 38 MB device copy and one graph
+    launch per step instead of ~900 kernels plus the autograd/hook Python, which is what bounds the step once the
+    kernels are fused (bench.py reports host_enqueue_ms_per_step).  Everything the graph needs to vary is
+    device-resident: hyper-parameters and loss scale (FusedSGD.hyper), signal sequence numbers (csrc/common.cuh), BN
+    accumulators.  Batches of another shape (last partial batch) fall back to the eager path.
+    """
+
+    def __init__(self, st, model, criterion, optimizer, metrics, use_graph: bool = False, warmup: int = 3):
+        self.st, self.model, self.criterion, self.optimizer, self.metrics = st, model, criterion, optimizer, metrics
+        self.use_graph = bool(use_graph) and torch.cuda.is_available()
+        self.warmup = warmup
+        self.calls = 0
+        self.graph = None
+        self.static_x = self.static_y = self.static_m = None
+
+    def _body(self, images, target, dev=None):
+        output = self.st.forward(self.model, images)
+        loss = self.criterion(output.float() if output.dtype != torch.float32 else output, target)
+        if dev is None:
+            self.metrics.push(output, target, loss, images.size(0))
+        else:
+            self.metrics.launch(output, target, loss, dev)
+        if dev is None:
+            self.optimizer.zero_grad()
+        self.st.backward(loss, self.optimizer)
+        self.optimizer.step()
+
+    def _capture(self, images, target):
+        self.static_x, self.static_y = images.clone(), target.clone()
+        self.static_m = torch.zeros(4, dtype=torch.float32, device=images.device)
+        self.optimizer.zero_grad(set_to_none=True)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._body(self.static_x, self.static_y, self.static_m)
+        self.graph = g
+
+    def __call__(self, images, target):
+        self.calls += 1
+        if self.use_graph and self.graph is None and self.calls > self.warmup and images.is_cuda:
+            self._capture(images, target)
+        if self.graph is not None and images.shape == self.static_x.shape and images.dtype == self.static_x.dtype:
+            self.static_x.copy_(images, non_blocking=True)
+            self.static_y.copy_(target, non_blocking=True)
+            if hasattr(self.optimizer, "refresh_hyper"):
+                self.optimizer.refresh_hyper()
+            self.graph.replay()
+            self.metrics.fetch(self.static_m, images.size(0))
+        else:
+            self._body(images, target)
+        self.metrics.poll()
+
+
 # ====================================================================== strategies
 class Strategy:
     """What differs between the reference scripts."""
@@ -156,6 +221,7 @@ class Strategy:
     reduce_metrics = True
     raw_uint8_loader = False
     cast_params = True          # low precision = cast the model (fp32 masters in FusedSGD); False => autocast
+    graph_capable = True        # the train step may be captured into a CUDA graph (--cuda-graph)
     epoch_csv: Optional[str] = None
 
     def init_process_group(self, args, local_rank: int, nprocs: int) -> None:
@@ -280,6 +346,7 @@ class HorovodStrategy(Strategy):
     """/root/reference/horovod_distributed.py: broadcast_parameters + DistributedOptimizer(compression=fp16)."""
     name = "horovod_distributed"
     cast_params = False         # gradients come back decompressed to fp32 into p.grad: keep fp32 weights + autocast
+    graph_capable = False       # the fusion dispatcher is a host thread: not capturable
 
     def init_process_group(self, args, local_rank, nprocs):
         from .parallel import hvd
@@ -313,6 +380,7 @@ class DataParallelStrategy(Strategy):
     distributed = False
     shard_batch = False
     reduce_metrics = False
+    graph_capable = False       # replica forwards run on host threads across devices
     epoch_csv = "dataparallel.csv"
 
     def init_process_group(self, args, local_rank, nprocs):
@@ -432,19 +500,17 @@ def train(train_loader, model, criterion, optimizer, epoch, st: Strategy, device
     progress = ProgressMeter(len(pf), [batch_time, data_time, losses, top1, top5], prefix="Epoch: [{}]".format(epoch))
     metrics = MetricPipeline(getattr(st, "comm", None), device, (losses, top1, top5), reduce=st.reduce_metrics)
     model.train()
+    step = getattr(st, "_train_step", None)
+    if step is None or step.model is not model:
+        step = st._train_step = TrainStep(st, model, criterion, optimizer, metrics, use_graph=args.cuda_graph and st.graph_capable)
+    step.metrics = metrics
     end = time.time()
     t0 = end
     n_img = 0
     for i, (images, target) in enumerate(pf):
         data_time.update(time.time() - end)
-        output = st.forward(model, images)
-        loss = criterion(output.float() if output.dtype != torch.float32 else output, target)
-        metrics.push(output, target, loss, images.size(0))
-        optimizer.zero_grad()
-        st.backward(loss, optimizer)
-        optimizer.step()
+        step(images, target)
         n_img += images.size(0)
-        metrics.poll()
         batch_time.update(time.time() - end)
         end = time.time()
         if i % args.print_freq == 0:

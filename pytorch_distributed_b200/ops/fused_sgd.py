@@ -80,6 +80,11 @@ class FusedSGD(Optimizer):
             ent[1] = vals
         return ent[0]
 
+    def refresh_hyper(self) -> None:
+        """Push changed lr/momentum/weight-decay to the device copies (needed when ``step`` is replayed from a CUDA graph)."""
+        for gi, ent in self._hyper.items():
+            self._hyper_tensor(gi, self.param_groups[gi], ent[0].device)
+
     # ------------------------------------------------------------------ step
     @torch.no_grad()
     def step(self, closure=None):
