@@ -190,10 +190,14 @@ class TrainStep:
         self.static_m = torch.zeros(4, dtype=torch.float32, device=images.device)
         self.optimizer.zero_grad(set_to_none=True)
         torch.cuda.synchronize()
+        from . import _ext
+        n0 = _ext.launches
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             self._body(self.static_x, self.static_y, self.static_m)
         self.graph = g
+        self.graph_launches = _ext.launches - n0      # native kernels inside the graph (capture enqueues, replay runs them)
+        _ext.launches = n0
 
     def __call__(self, images, target):
         self.calls += 1
@@ -205,6 +209,8 @@ class TrainStep:
             if hasattr(self.optimizer, "refresh_hyper"):
                 self.optimizer.refresh_hyper()
             self.graph.replay()
+            from . import _ext
+            _ext.note_launch(self.graph_launches)
             self.metrics.fetch(self.static_m, images.size(0))
         else:
             self._body(images, target)
