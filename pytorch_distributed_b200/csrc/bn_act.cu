@@ -579,10 +579,12 @@ __global__ void __launch_bounds__(kBnThreads) stem_fwd_kernel(const T* __restric
   }
   const int64_t total = (int64_t)N * g.OH * g.OW;
   const int ppb = blockDim.x / cgs;                  // output pixels per CTA pass
-  for (int64_t p = (int64_t)blockIdx.x * ppb + threadIdx.x / cgs; p < total; p += (int64_t)gridDim.x * ppb) {
-    const int ow = (int)(p % g.OW);
-    const int oh = (int)((p / g.OW) % g.OH);
-    const int64_t n = p / ((int64_t)g.OW * g.OH);
+  // 32-bit index math (host checks the pixel counts fit): 64-bit div/mod would dominate the instruction stream
+  for (int p = blockIdx.x * ppb + threadIdx.x / cgs; p < (int)total; p += gridDim.x * ppb) {
+    const int ow = p % g.OW;
+    const int t_ = p / g.OW;
+    const int oh = t_ % g.OH;
+    const int64_t n = t_ / g.OH;
     float best[8];
     uint32_t sel[8];
 #pragma unroll
@@ -605,12 +607,12 @@ __global__ void __launch_bounds__(kBnThreads) stem_fwd_kernel(const T* __restric
         }
       }
     }
-    store8<T>(y + p * C + cg * 8, best);
+    store8<T>(y + (int64_t)p * C + cg * 8, best);
     if (code) {
       uint32_t word = 0;
 #pragma unroll
       for (int k = 0; k < 8; ++k) word |= sel[k] << (4 * k);
-      code[p * cgs + cg] = word;
+      code[(int64_t)p * cgs + cg] = word;
     }
   }
 }
@@ -655,12 +657,12 @@ __global__ void __launch_bounds__(kBnThreads) stem_bwd_reduce_kernel(const T* __
       float mean[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) mean[k] = saved[cg * 8 + k];
-      for (int64_t r = r0 + m.rlocal; r < r1; r += m.rpp) {
-        const int iw = (int)(r % g.W), ih = (int)((r / g.W) % g.H);
-        const int64_t n = r / ((int64_t)g.W * g.H);
+      for (int r = (int)r0 + m.rlocal; r < (int)r1; r += m.rpp) {
+        const int iw = r % g.W, t_ = r / g.W, ih = t_ % g.H;
+        const int64_t n = t_ / g.H;
         float dz[8], v[8];
         stem_gather_dz<T>(dp, code, n, ih, iw, cg, m.cgs, C, g, dz);
-        load8<T>(x + r * C + cg * 8, v);
+        load8<T>(x + (int64_t)r * C + cg * 8, v);
 #pragma unroll
         for (int k = 0; k < 8; ++k) { s[k] += dz[k]; q[k] += dz[k] * (v[k] - mean[k]); }
       }
@@ -695,16 +697,16 @@ __global__ void __launch_bounds__(kBnThreads) stem_bwd_apply_kernel(const T* __r
         st_w(db, wdt, c, sdz);
       }
     }
-    const int64_t stride = (int64_t)gridDim.x * m.rpp;
-    for (int64_t r = (int64_t)blockIdx.x * m.rpp + m.rlocal; r < M; r += stride) {
-      const int iw = (int)(r % g.W), ih = (int)((r / g.W) % g.H);
-      const int64_t n = r / ((int64_t)g.W * g.H);
+    const int stride = gridDim.x * m.rpp;
+    for (int r = blockIdx.x * m.rpp + m.rlocal; r < (int)M; r += stride) {
+      const int iw = r % g.W, t_ = r / g.W, ih = t_ % g.H;
+      const int64_t n = t_ / g.H;
       float dz[8], v[8];
       stem_gather_dz<T>(dp, code, n, ih, iw, cg, m.cgs, C, g, dz);
-      load8<T>(x + r * C + cg * 8, v);
+      load8<T>(x + (int64_t)r * C + cg * 8, v);
 #pragma unroll
       for (int k = 0; k < 8; ++k) v[k] = ka[k] * dz[k] + kb[k] * v[k] + kd[k];
-      store8<T>(dx + r * C + cg * 8, v);
+      store8<T>(dx + (int64_t)r * C + cg * 8, v);
     }
   }
 }
@@ -752,6 +754,7 @@ std::vector<at::Tensor> stem_forward(const at::Tensor& x, const at::Tensor& weig
   check_nhwc(x, "x");
   const int C = (int)x.size(1);
   TORCH_CHECK(C % 8 == 0 && kBnThreads % (C / 8) == 0, "fused stem needs C/8 to divide ", kBnThreads);
+  TORCH_CHECK(x.numel() / C < (int64_t)1 << 30, "fused stem: too many pixels for 32-bit indexing");
   TORCH_CHECK(training || running_mean.defined(), "eval mode needs running statistics");
   c10::cuda::CUDAGuard guard(x.device());
   const PoolGeom pg = pool_geom(x);

@@ -52,7 +52,20 @@ template <typename W, typename S>
 __device__ __forceinline__ void pack_seg(const S* __restrict__ src, W* __restrict__ dst, int len, float scale) {
   const bool aligned = ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
   const int nvec = aligned ? (len >> 3) : 0;
-  for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+  int v = threadIdx.x;
+  // 4 independent 16/32-byte loads in flight per thread: a 32-CTA kernel has to pull its weight on HBM
+  for (; v + 3 * (int)blockDim.x < nvec; v += 4 * blockDim.x) {
+    float f[4][8];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) load8<S>(src + ((v + u * (int)blockDim.x) << 3), f[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[u][k] *= scale;
+      store8<W>(dst + ((v + u * (int)blockDim.x) << 3), f[u]);
+    }
+  }
+  for (; v < nvec; v += blockDim.x) {
     float f[8];
     load8<S>(src + (v << 3), f);
 #pragma unroll
@@ -67,7 +80,21 @@ __device__ __forceinline__ bool unpack_seg(const W* __restrict__ src, D* __restr
   const bool aligned = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
   const int nvec = aligned ? (len >> 3) : 0;
   bool bad = false;
-  for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+  int v = threadIdx.x;
+  for (; v + 3 * (int)blockDim.x < nvec; v += 4 * blockDim.x) {
+    float f[4][8];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) load8<W>(src + ((v + u * (int)blockDim.x) << 3), f[u], /*sys=*/true);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (check) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) bad |= !isfinite(f[u][k]);
+      }
+      store8<D>(dst + ((v + u * (int)blockDim.x) << 3), f[u]);
+    }
+  }
+  for (; v < nvec; v += blockDim.x) {
     float f[8];
     load8<W>(src + (v << 3), f, /*sys=*/true);
     if (check) {
