@@ -286,6 +286,8 @@ class Strategy:
                                         comm=self.comm_kind(args, device), wire_dtype=wire, bucket_cap_mb=args.bucket_cap_mb)
         self.comm = model.comm
         self.engine = model.engine
+        from .utils.dist_ops import set_default_communicator
+        set_default_communicator(self.comm)
         return model
 
     def build(self, model, args, device, local_rank):

@@ -171,6 +171,17 @@ class DataPrefetcher:
             img = self._convert(img)
         return img, tgt
 
+    def next(self):
+        """Reference-style pull API (``data_prefetcher.next()`` in /root/reference/apex_distributed.py:160-169):
+        returns ``(input, target)`` and ``(None, None)`` when the loader is exhausted."""
+        if getattr(self, "_gen", None) is None:
+            self._gen = iter(self)
+        try:
+            return next(self._gen)
+        except StopIteration:
+            self._gen = None
+            return None, None
+
     def __iter__(self):
         it = iter(_limited(self.loader, self.limit))
         nxt = None
@@ -189,3 +200,6 @@ class DataPrefetcher:
             except StopIteration:
                 nxt = None
             yield cur
+
+
+data_prefetcher = DataPrefetcher   # the reference's class name
