@@ -103,7 +103,9 @@ __global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const T* __restric
                                                               int rows_per_block) {
   extern __shared__ float sm[];
   const RowMap m = row_map(C);
-  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = min(M, r0 + (int64_t)rows_per_block);
+  // CTAs are dispatched in blockIdx order; walking the tensor BACK to FRONT makes the first CTAs read what the producer
+  // wrote last (still in the 126 MB L2) and leaves the FRONT of the tensor in L2 for the apply pass, which walks forward.
+  const int64_t r0 = (int64_t)(gridDim.x - 1 - blockIdx.x) * rows_per_block, r1 = min(M, r0 + (int64_t)rows_per_block);
   for (int cgb = 0; cgb < m.cgs; cgb += m.tpr) {
     const int cg = cgb + m.cg0;
     float s[8], q[8];
@@ -221,7 +223,9 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(const T* __re
                                                                    float* __restrict__ gsum, int64_t M, int C, int rows_per_block) {
   extern __shared__ float sm[];
   const RowMap m = row_map(C);
-  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = min(M, r0 + (int64_t)rows_per_block);
+  // CTAs are dispatched in blockIdx order; walking the tensor BACK to FRONT makes the first CTAs read what the producer
+  // wrote last (still in the 126 MB L2) and leaves the FRONT of the tensor in L2 for the apply pass, which walks forward.
+  const int64_t r0 = (int64_t)(gridDim.x - 1 - blockIdx.x) * rows_per_block, r1 = min(M, r0 + (int64_t)rows_per_block);
   for (int cgb = 0; cgb < m.cgs; cgb += m.tpr) {
     const int cg = cgb + m.cg0;
     float s[8], q[8];
@@ -378,9 +382,8 @@ static Geometry geometry(const at::Tensor& x) {
   return g;
 }
 static int reduce_grid(const Geometry& g, int* rows_per_block) {
-  // enough CTAs to fill the machine (>= 4 per SM when the tensor is big), but >= 32 row-passes per CTA so the
-  // combine/atomic tail stays small
-  int64_t blocks = (g.M + (int64_t)g.rpp * 32 - 1) / ((int64_t)g.rpp * 32);
+  // enough CTAs to fill the machine even for the 12 MB layer-4 tensors (>= 8 row-passes per CTA), capped at 8 per SM
+  int64_t blocks = (g.M + (int64_t)g.rpp * 8 - 1) / ((int64_t)g.rpp * 8);
   blocks = std::max<int64_t>(std::min<int64_t>(blocks, (int64_t)g.sms * 8), 1);
   int64_t rpb = (g.M + blocks - 1) / blocks;
   rpb = (rpb + g.rpp - 1) / g.rpp * g.rpp;
@@ -553,7 +556,7 @@ __device__ __forceinline__ void stem_scale_shift(const float* gsum, const float*
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kBnThreads) stem_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, uint32_t* __restrict__ code,
+__global__ void __launch_bounds__(kBnThreads) stem_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, uint2* __restrict__ code,
                                                               const float* __restrict__ gsum, const void* __restrict__ w,
                                                               const void* __restrict__ b, int wdt, float* __restrict__ running_mean,
                                                               float* __restrict__ running_var, int64_t* __restrict__ nbt,
@@ -608,105 +611,241 @@ __global__ void __launch_bounds__(kBnThreads) stem_fwd_kernel(const T* __restric
       }
     }
     store8<T>(y + (int64_t)p * C + cg * 8, best);
-    if (code) {
-      uint32_t word = 0;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) word |= sel[k] << (4 * k);
+    if (code) {   // one byte per channel: the backward compares 4 channels per instruction (vcmpeq4)
+      uint2 word;
+      word.x = sel[0] | (sel[1] << 8) | (sel[2] << 16) | (sel[3] << 24);
+      word.y = sel[4] | (sel[5] << 8) | (sel[6] << 16) | (sel[7] << 24);
       code[(int64_t)p * cgs + cg] = word;
     }
   }
 }
 
-// dz (gradient w.r.t. the BN+ReLU output at one input position) = sum of the pooled gradients that selected it
+// dz (gradient w.r.t. the BN+ReLU output at one input position) = sum of the pooled gradients that selected it.
+// 16-bit dtypes stay packed: vcmpeq4 turns the 8 arg-max bytes into byte masks, PRMT widens them to 16-bit lane masks,
+// the masked bf16x2/half2 pairs are accumulated with packed adds (at most 4 terms) and widened to fp32 once.
+template <typename T> struct Pair;
+template <> struct Pair<__nv_bfloat16> {
+  using P = __nv_bfloat162;
+  static __device__ __forceinline__ uint32_t add(uint32_t a, uint32_t b) {
+    P r = __hadd2(*reinterpret_cast<P*>(&a), *reinterpret_cast<P*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+  }
+  static __device__ __forceinline__ float2 widen(uint32_t a) { return __bfloat1622float2(*reinterpret_cast<P*>(&a)); }
+};
+template <> struct Pair<__half> {
+  using P = __half2;
+  static __device__ __forceinline__ uint32_t add(uint32_t a, uint32_t b) {
+    P r = __hadd2(*reinterpret_cast<P*>(&a), *reinterpret_cast<P*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+  }
+  static __device__ __forceinline__ float2 widen(uint32_t a) { return __half22float2(*reinterpret_cast<P*>(&a)); }
+};
+
 template <typename T>
-__device__ __forceinline__ void stem_gather_dz(const T* __restrict__ dp, const uint32_t* __restrict__ code, int64_t n, int ih, int iw, int cg,
+__device__ __forceinline__ void stem_gather_dz(const T* __restrict__ dp, const uint2* __restrict__ code, int64_t n, int ih, int iw, int cg,
                                                int cgs, int C, const PoolGeom& g, float (&dz)[8]) {
-#pragma unroll
-  for (int k = 0; k < 8; ++k) dz[k] = 0.f;
   const int oh0 = ih >> 1, oh1 = min((ih + 1) >> 1, g.OH - 1);
   const int ow0 = iw >> 1, ow1 = min((iw + 1) >> 1, g.OW - 1);
-  for (int oh = oh0; oh <= oh1; ++oh) {
-    const int kh = ih - (2 * oh - 1);
-    for (int ow = ow0; ow <= ow1; ++ow) {
-      const int kw = iw - (2 * ow - 1);
-      const uint32_t want = (uint32_t)(kh * 3 + kw);
-      const int64_t p = (n * g.OH + oh) * g.OW + ow;
-      const uint32_t word = code[p * cgs + cg];
-      float d[8];
-      load8<T>(dp + p * C + cg * 8, d);
+  if constexpr (sizeof(T) == 2) {
+    uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;      // +0.0 pairs
+    for (int oh = oh0; oh <= oh1; ++oh) {
+      const int kh = ih - (2 * oh - 1);
+      for (int ow = ow0; ow <= ow1; ++ow) {
+        const uint32_t pat = (uint32_t)(kh * 3 + iw - (2 * ow - 1)) * 0x01010101u;
+        const int64_t p = (n * g.OH + oh) * g.OW + ow;
+        const uint2 cw = code[p * cgs + cg];
+        const V4 d = ld_stream(dp + p * C + cg * 8);
+        const uint32_t m0 = __vcmpeq4(cw.x, pat), m1 = __vcmpeq4(cw.y, pat);
+        a0 = Pair<T>::add(a0, d.x & __byte_perm(m0, 0, 0x1100));
+        a1 = Pair<T>::add(a1, d.y & __byte_perm(m0, 0, 0x3322));
+        a2 = Pair<T>::add(a2, d.z & __byte_perm(m1, 0, 0x1100));
+        a3 = Pair<T>::add(a3, d.w & __byte_perm(m1, 0, 0x3322));
+      }
+    }
+    float2 t;
+    t = Pair<T>::widen(a0); dz[0] = t.x; dz[1] = t.y;
+    t = Pair<T>::widen(a1); dz[2] = t.x; dz[3] = t.y;
+    t = Pair<T>::widen(a2); dz[4] = t.x; dz[5] = t.y;
+    t = Pair<T>::widen(a3); dz[6] = t.x; dz[7] = t.y;
+  } else {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) dz[k] += ((word >> (4 * k)) & 15u) == want ? d[k] : 0.f;
+    for (int k = 0; k < 8; ++k) dz[k] = 0.f;
+    for (int oh = oh0; oh <= oh1; ++oh) {
+      const int kh = ih - (2 * oh - 1);
+      for (int ow = ow0; ow <= ow1; ++ow) {
+        const uint32_t want = (uint32_t)(kh * 3 + iw - (2 * ow - 1));
+        const int64_t p = (n * g.OH + oh) * g.OW + ow;
+        const uint2 cw = code[p * cgs + cg];
+        float d[8];
+        load8<T>(dp + p * C + cg * 8, d);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t sel = ((k < 4 ? cw.x : cw.y) >> (8 * (k & 3))) & 255u;
+          dz[k] += sel == want ? d[k] : 0.f;
+        }
+      }
+    }
+  }
+}
+
+// Backward over 2x2 QUADS of input positions.  The four positions (2k..2k+1, 2j..2j+1) are covered by exactly four
+// pooling windows A=(k,j) B=(k,j+1) C=(k+1,j) D=(k+1,j+1); each window's (arg-max bytes, pooled gradient) is loaded ONCE
+// per quad and matched against the nine (window, position) slots:
+//     dz00 = A@4        dz01 = A@5 + B@3        dz10 = A@7 + C@1        dz11 = A@8 + B@6 + C@2 + D@0
+// so every lane does the same work (no parity divergence) and the per-position instruction count drops ~5x versus a
+// per-position gather.  A CTA owns `rows_per_block` quad rows (n, k): n and k are CTA-uniform scalars.
+template <typename T>
+struct QuadDz {                                         // packed accumulators: 4 positions x 4 pair-words
+  uint32_t a[4][4];
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) a[i][j] = 0u;
+  }
+  __device__ __forceinline__ void hit(int pos, const uint2& cw, const V4& d, uint32_t want) {
+    const uint32_t pat = want * 0x01010101u;
+    const uint32_t m0 = __vcmpeq4(cw.x, pat), m1 = __vcmpeq4(cw.y, pat);
+    a[pos][0] = Pair<T>::add(a[pos][0], d.x & __byte_perm(m0, 0, 0x1100));
+    a[pos][1] = Pair<T>::add(a[pos][1], d.y & __byte_perm(m0, 0, 0x3322));
+    a[pos][2] = Pair<T>::add(a[pos][2], d.z & __byte_perm(m1, 0, 0x1100));
+    a[pos][3] = Pair<T>::add(a[pos][3], d.w & __byte_perm(m1, 0, 0x3322));
+  }
+  __device__ __forceinline__ void widen(int pos, float (&dz)[8]) const {
+    float2 t;
+    t = Pair<T>::widen(a[pos][0]); dz[0] = t.x; dz[1] = t.y;
+    t = Pair<T>::widen(a[pos][1]); dz[2] = t.x; dz[3] = t.y;
+    t = Pair<T>::widen(a[pos][2]); dz[4] = t.x; dz[5] = t.y;
+    t = Pair<T>::widen(a[pos][3]); dz[6] = t.x; dz[7] = t.y;
+  }
+};
+
+// dz of the quad (n, k, j) for channel group cg; 16-bit dtypes only (fp32 uses the per-position gather)
+template <typename T>
+__device__ __forceinline__ void stem_quad_dz(const T* __restrict__ dp, const uint2* __restrict__ code, int64_t n, int k, int j, int cg, int cgs,
+                                             int C, const PoolGeom& g, QuadDz<T>& qd) {
+  qd.clear();
+  const bool has_r = (j + 1) < g.OW, has_b = (k + 1) < g.OH;
+  const int64_t pA = (n * g.OH + k) * g.OW + j;
+  {
+    const uint2 cw = code[pA * cgs + cg];
+    const V4 d = ld_stream(dp + pA * C + cg * 8);
+    qd.hit(0, cw, d, 4u); qd.hit(1, cw, d, 5u); qd.hit(2, cw, d, 7u); qd.hit(3, cw, d, 8u);
+  }
+  if (has_r) {
+    const uint2 cw = code[(pA + 1) * cgs + cg];
+    const V4 d = ld_stream(dp + (pA + 1) * C + cg * 8);
+    qd.hit(1, cw, d, 3u); qd.hit(3, cw, d, 6u);
+  }
+  if (has_b) {
+    const int64_t pC = pA + g.OW;
+    const uint2 cw = code[pC * cgs + cg];
+    const V4 d = ld_stream(dp + pC * C + cg * 8);
+    qd.hit(2, cw, d, 1u); qd.hit(3, cw, d, 2u);
+    if (has_r) {
+      const uint2 cw2 = code[(pC + 1) * cgs + cg];
+      const V4 d2 = ld_stream(dp + (pC + 1) * C + cg * 8);
+      qd.hit(3, cw2, d2, 0u);
     }
   }
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kBnThreads) stem_bwd_reduce_kernel(const T* __restrict__ dp, const uint32_t* __restrict__ code,
+__global__ void __launch_bounds__(kBnThreads) stem_bwd_reduce_kernel(const T* __restrict__ dp, const uint2* __restrict__ code,
                                                                      const T* __restrict__ x, const float* __restrict__ saved,
                                                                      float* __restrict__ gsum, int64_t M, int C, PoolGeom g,
                                                                      int rows_per_block) {
   extern __shared__ float sm[];
-  const RowMap m = row_map(C);
-  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = min(M, r0 + (int64_t)rows_per_block);
-  for (int cgb = 0; cgb < m.cgs; cgb += m.tpr) {
-    const int cg = cgb + m.cg0;
-    float s[8], q[8];
+  const RowMap m = row_map(C);                       // tpr == cgs (host guarantees cgs divides the CTA size)
+  const int cg = m.cg0;
+  const int QH = (g.H + 1) >> 1, QW = (g.W + 1) >> 1;
+  const int nrows = (int)(M / ((int64_t)g.H * g.W)) * QH;   // quad rows
+  const int row0 = blockIdx.x * rows_per_block, row1 = min(nrows, row0 + rows_per_block);
+  float s[8], q[8], mean[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { s[k] = 0.f; q[k] = 0.f; }
-    if (m.active && cg < m.cgs) {
-      float mean[8];
+  for (int k = 0; k < 8; ++k) { s[k] = 0.f; q[k] = 0.f; mean[k] = saved[cg * 8 + k]; }
+  for (int row = row0; row < row1; ++row) {
+    const int n = row / QH, k = row - n * QH;
+    for (int j = m.rlocal; j < QW; j += m.rpp) {
+      if constexpr (sizeof(T) == 2) {
+        QuadDz<T> qd;
+        stem_quad_dz<T>(dp, code, n, k, j, cg, m.cgs, C, g, qd);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) mean[k] = saved[cg * 8 + k];
-      for (int r = (int)r0 + m.rlocal; r < (int)r1; r += m.rpp) {
-        const int iw = r % g.W, t_ = r / g.W, ih = t_ % g.H;
-        const int64_t n = t_ / g.H;
-        float dz[8], v[8];
-        stem_gather_dz<T>(dp, code, n, ih, iw, cg, m.cgs, C, g, dz);
-        load8<T>(x + (int64_t)r * C + cg * 8, v);
+        for (int pos = 0; pos < 4; ++pos) {
+          const int ih = 2 * k + (pos >> 1), iw = 2 * j + (pos & 1);
+          if (ih < g.H && iw < g.W) {
+            float dz[8], v[8];
+            qd.widen(pos, dz);
+            load8<T>(x + (((int64_t)n * g.H + ih) * g.W + iw) * C + cg * 8, v);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { s[k] += dz[k]; q[k] += dz[k] * (v[k] - mean[k]); }
+            for (int c = 0; c < 8; ++c) { s[c] += dz[c]; q[c] += dz[c] * (v[c] - mean[c]); }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int pos = 0; pos < 4; ++pos) {
+          const int ih = 2 * k + (pos >> 1), iw = 2 * j + (pos & 1);
+          if (ih < g.H && iw < g.W) {
+            float dz[8], v[8];
+            stem_gather_dz<T>(dp, code, n, ih, iw, cg, m.cgs, C, g, dz);
+            load8<T>(x + (((int64_t)n * g.H + ih) * g.W + iw) * C + cg * 8, v);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) { s[c] += dz[c]; q[c] += dz[c] * (v[c] - mean[c]); }
+          }
+        }
       }
-#pragma unroll
-      for (int k = 0; k < 8; ++k) q[k] *= saved[C + cg * 8 + k];
     }
-    cta_combine(m, cgb, s, q, sm, gsum, C);
   }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) q[k] *= saved[C + cg * 8 + k];
+  cta_combine(m, 0, s, q, sm, gsum, C);
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kBnThreads) stem_bwd_apply_kernel(const T* __restrict__ dp, const uint32_t* __restrict__ code,
+__global__ void __launch_bounds__(kBnThreads) stem_bwd_apply_kernel(const T* __restrict__ dp, const uint2* __restrict__ code,
                                                                     const T* __restrict__ x, const float* __restrict__ saved,
                                                                     const float* __restrict__ gsum, const void* __restrict__ w, int wdt,
                                                                     T* __restrict__ dx, void* __restrict__ dw, void* __restrict__ db,
-                                                                    int64_t M, int C, PoolGeom g) {
+                                                                    int64_t M, int C, PoolGeom g, int rows_per_block) {
   const RowMap m = row_map(C);
-  if (!m.active) return;
+  const int cg = m.cg0;
   const float inv_m = 1.f / (float)M;
-  for (int cg = m.cg0; cg < m.cgs; cg += m.tpr) {
-    float ka[8], kb[8], kd[8];
+  float ka[8], kb[8], kd[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int c = cg * 8 + k;
-      const float mean = saved[c], invstd = saved[C + c];
-      const float sdz = gsum[c], sdzx = gsum[C + c];
-      ka[k] = ld_w(w, wdt, c) * invstd;
-      kb[k] = -ka[k] * invstd * sdzx * inv_m;
-      kd[k] = -ka[k] * sdz * inv_m - kb[k] * mean;
-      if (blockIdx.x == 0 && m.rlocal == 0) {
-        st_w(dw, wdt, c, sdzx);
-        st_w(db, wdt, c, sdz);
-      }
+  for (int k = 0; k < 8; ++k) {
+    const int c = cg * 8 + k;
+    const float mean = saved[c], invstd = saved[C + c];
+    const float sdz = gsum[c], sdzx = gsum[C + c];
+    ka[k] = ld_w(w, wdt, c) * invstd;
+    kb[k] = -ka[k] * invstd * sdzx * inv_m;
+    kd[k] = -ka[k] * sdz * inv_m - kb[k] * mean;
+    if (blockIdx.x == 0 && m.rlocal == 0) {
+      st_w(dw, wdt, c, sdzx);
+      st_w(db, wdt, c, sdz);
     }
-    const int stride = gridDim.x * m.rpp;
-    for (int r = blockIdx.x * m.rpp + m.rlocal; r < (int)M; r += stride) {
-      const int iw = r % g.W, t_ = r / g.W, ih = t_ % g.H;
-      const int64_t n = t_ / g.H;
-      float dz[8], v[8];
-      stem_gather_dz<T>(dp, code, n, ih, iw, cg, m.cgs, C, g, dz);
-      load8<T>(x + (int64_t)r * C + cg * 8, v);
+  }
+  const int QH = (g.H + 1) >> 1, QW = (g.W + 1) >> 1;
+  const int nrows = (int)(M / ((int64_t)g.H * g.W)) * QH;
+  const int row0 = blockIdx.x * rows_per_block, row1 = min(nrows, row0 + rows_per_block);
+  for (int row = row0; row < row1; ++row) {
+    const int n = row / QH, k = row - n * QH;
+    for (int j = m.rlocal; j < QW; j += m.rpp) {
+      QuadDz<T> qd;
+      if constexpr (sizeof(T) == 2) stem_quad_dz<T>(dp, code, n, k, j, cg, m.cgs, C, g, qd);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = ka[k] * dz[k] + kb[k] * v[k] + kd[k];
-      store8<T>(dx + (int64_t)r * C + cg * 8, v);
+      for (int pos = 0; pos < 4; ++pos) {
+        const int ih = 2 * k + (pos >> 1), iw = 2 * j + (pos & 1);
+        if (ih < g.H && iw < g.W) {
+          float dz[8], v[8];
+          if constexpr (sizeof(T) == 2) qd.widen(pos, dz);
+          else stem_gather_dz<T>(dp, code, n, ih, iw, cg, m.cgs, C, g, dz);
+          const int64_t off = (((int64_t)n * g.H + ih) * g.W + iw) * C + cg * 8;
+          load8<T>(x + off, v);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) v[c] = ka[c] * dz[c] + kb[c] * v[c] + kd[c];
+          store8<T>(dx + off, v);
+        }
+      }
     }
   }
 }
@@ -739,7 +878,7 @@ static void stem_fwd_impl(const at::Tensor& x, at::Tensor& y, at::Tensor& code, 
   const int ppb = kBnThreads / cgs;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((total + ppb - 1) / ppb, (int64_t)g.sms * 16));
   stem_fwd_kernel<T><<<grid, kBnThreads, 0, st>>>(xp, reinterpret_cast<T*>(y.data_ptr()),
-                                                 code.defined() ? reinterpret_cast<uint32_t*>(code.data_ptr()) : nullptr, wk, w.data_ptr(),
+                                                 code.defined() ? reinterpret_cast<uint2*>(code.data_ptr()) : nullptr, wk, w.data_ptr(),
                                                  b.data_ptr(), wdtype(w), rm.defined() ? rm.data_ptr<float>() : nullptr,
                                                  rv.defined() ? rv.data_ptr<float>() : nullptr, nbt.defined() ? nbt.data_ptr<int64_t>() : nullptr,
                                                  saved.defined() ? saved.data_ptr<float>() : nullptr, g.M, (int)x.size(0), g.C, pg, eps, momentum,
@@ -765,7 +904,7 @@ std::vector<at::Tensor> stem_forward(const at::Tensor& x, const at::Tensor& weig
     TORCH_CHECK(work.defined() && work.numel() >= 2 * C, "work buffer too small");
     saved = at::empty({2 * C}, x.options().dtype(at::kFloat));
   }
-  if (need_code) code = at::empty({y.numel() / 8}, x.options().dtype(at::kInt));
+  if (need_code) code = at::empty({y.numel()}, x.options().dtype(at::kByte));
   switch (x.scalar_type()) {
     case at::kBFloat16: stem_fwd_impl<__nv_bfloat16>(x, y, code, work, saved, weight, bias, running_mean, running_var, nbt, training, (float)momentum, (float)eps); break;
     case at::kHalf: stem_fwd_impl<__half>(x, y, code, work, saved, weight, bias, running_mean, running_var, nbt, training, (float)momentum, (float)eps); break;
@@ -782,15 +921,15 @@ static void stem_bwd_impl(const at::Tensor& dp, const at::Tensor& code, const at
   const PoolGeom pg = pool_geom(x);
   cudaStream_t st = at::cuda::getCurrentCUDAStream();
   const T* dpp = reinterpret_cast<const T*>(dp.data_ptr());
-  const uint32_t* cp = reinterpret_cast<const uint32_t*>(code.data_ptr());
+  const uint2* cp = reinterpret_cast<const uint2*>(code.data_ptr());
   const T* xp = reinterpret_cast<const T*>(x.data_ptr());
-  int rpb;
-  const int rgrid = reduce_grid(g, &rpb);
-  stem_bwd_reduce_kernel<T><<<rgrid, kBnThreads, g.smem, st>>>(dpp, cp, xp, saved.data_ptr<float>(), work.data_ptr<float>(), g.M, g.C, pg, rpb);
+  const int nrows = (int)(x.size(0) * ((pg.H + 1) / 2));               // quad rows
+  const int rpb = std::max(1, std::min(4, nrows / (g.sms * 8)));       // quad rows per CTA
+  const int grid = (nrows + rpb - 1) / rpb;
+  stem_bwd_reduce_kernel<T><<<grid, kBnThreads, g.smem, st>>>(dpp, cp, xp, saved.data_ptr<float>(), work.data_ptr<float>(), g.M, g.C, pg, rpb);
   C10_CUDA_KERNEL_LAUNCH_CHECK();
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((g.M + g.rpp - 1) / g.rpp, (int64_t)g.sms * 16));
   stem_bwd_apply_kernel<T><<<grid, kBnThreads, 0, st>>>(dpp, cp, xp, saved.data_ptr<float>(), work.data_ptr<float>(), w.data_ptr(), wdtype(w),
-                                                       reinterpret_cast<T*>(dx.data_ptr()), dw.data_ptr(), db.data_ptr(), g.M, g.C, pg);
+                                                       reinterpret_cast<T*>(dx.data_ptr()), dw.data_ptr(), db.data_ptr(), g.M, g.C, pg, rpb);
   C10_CUDA_KERNEL_LAUNCH_CHECK();
 }
 
@@ -800,7 +939,7 @@ std::vector<at::Tensor> stem_backward(const at::Tensor& dp_in, const at::Tensor&
   check_nhwc(x, "x");
   at::Tensor dp = dp_in.is_contiguous(at::MemoryFormat::ChannelsLast) ? dp_in : dp_in.contiguous(at::MemoryFormat::ChannelsLast);
   const int C = (int)x.size(1);
-  TORCH_CHECK(dp.scalar_type() == x.scalar_type() && dp.size(1) == C && code.scalar_type() == at::kInt && code.numel() == dp.numel() / 8);
+  TORCH_CHECK(dp.scalar_type() == x.scalar_type() && dp.size(1) == C && code.scalar_type() == at::kByte && code.numel() == dp.numel());
   TORCH_CHECK(work.defined() && work.numel() >= 2 * C, "work buffer too small");
   c10::cuda::CUDAGuard guard(x.device());
   at::Tensor dx = at::empty_like(x, x.options().memory_format(at::MemoryFormat::ChannelsLast));
