@@ -103,9 +103,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const T* __restric
                                                               int rows_per_block) {
   extern __shared__ float sm[];
   const RowMap m = row_map(C);
-  // CTAs are dispatched in blockIdx order; walking the tensor BACK to FRONT makes the first CTAs read what the producer
-  // wrote last (still in the 126 MB L2) and leaves the FRONT of the tensor in L2 for the apply pass, which walks forward.
-  const int64_t r0 = (int64_t)(gridDim.x - 1 - blockIdx.x) * rows_per_block, r1 = min(M, r0 + (int64_t)rows_per_block);
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = min(M, r0 + (int64_t)rows_per_block);
   for (int cgb = 0; cgb < m.cgs; cgb += m.tpr) {
     const int cg = cgb + m.cg0;
     float s[8], q[8];
@@ -223,9 +221,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(const T* __re
                                                                    float* __restrict__ gsum, int64_t M, int C, int rows_per_block) {
   extern __shared__ float sm[];
   const RowMap m = row_map(C);
-  // CTAs are dispatched in blockIdx order; walking the tensor BACK to FRONT makes the first CTAs read what the producer
-  // wrote last (still in the 126 MB L2) and leaves the FRONT of the tensor in L2 for the apply pass, which walks forward.
-  const int64_t r0 = (int64_t)(gridDim.x - 1 - blockIdx.x) * rows_per_block, r1 = min(M, r0 + (int64_t)rows_per_block);
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = min(M, r0 + (int64_t)rows_per_block);
   for (int cgb = 0; cgb < m.cgs; cgb += m.tpr) {
     const int cg = cgb + m.cg0;
     float s[8], q[8];
