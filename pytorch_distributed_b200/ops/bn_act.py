@@ -68,12 +68,11 @@ def begin_step(device) -> None:
 
 class _BnActFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, residual, weight, bias, running_mean, running_var, nbt, training, momentum, eps, relu):
+    def forward(ctx, x, residual, weight, bias, running_mean, running_var, nbt, training, momentum, eps, relu, need_grad):
         from .. import _ext
         C = _ext.lib()
         nc = x.size(1)
         ws = workspace(x.device)
-        need_grad = any(ctx.needs_input_grad[:4])
         if training:
             work, gen = ws.take(4 * nc)
         else:
@@ -102,7 +101,7 @@ class _BnActFn(torch.autograd.Function):
             work = torch.zeros(2 * x.size(1), dtype=torch.float32, device=x.device)   # slice was recycled: use a fresh one
         _ext.note_launch(2)
         dx, dres, dw, db = C.bn_act_backward(dy, x, mask, weight, saved, ctx.relu, ctx.has_res, work)
-        return dx, (dres if ctx.has_res else None), dw, db, None, None, None, None, None, None, None
+        return dx, (dres if ctx.has_res else None), dw, db, None, None, None, None, None, None, None, None
 
 
 def _can_fuse(x, weight, residual, running_mean=True) -> bool:
@@ -125,7 +124,11 @@ def bn_act(x, weight, bias, running_mean, running_var, residual: Optional[torch.
         if training and num_batches_tracked is not None:
             num_batches_tracked.add_(1)
         return bn_act_reference(x, weight, bias, running_mean, running_var, residual, relu, training, momentum, eps)
-    if not training and running_mean is None:
-        raise ValueError("eval mode needs running statistics")
+    need_grad = torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad or bias.requires_grad
+                                             or (residual is not None and residual.requires_grad))
+    if need_grad and not training:      # backward through frozen (eval-mode) statistics: rare, use the composition
+        return bn_act_reference(x, weight.to(x.dtype) if weight.dtype != torch.float32 else weight,
+                                bias.to(x.dtype) if bias.dtype != torch.float32 else bias, running_mean, running_var, residual, relu,
+                                training, momentum, eps)
     return _BnActFn.apply(x, residual, weight, bias, running_mean, running_var, num_batches_tracked, training, float(momentum),
-                          float(eps), relu)
+                          float(eps), relu, need_grad)

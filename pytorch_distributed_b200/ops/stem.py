@@ -18,12 +18,11 @@ def bn_relu_maxpool_reference(x, weight, bias, running_mean, running_var, traini
 
 class _StemFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, running_mean, running_var, nbt, training, momentum, eps):
+    def forward(ctx, x, weight, bias, running_mean, running_var, nbt, training, momentum, eps, need_grad):
         from .. import _ext
         C = _ext.lib()
         nc = x.size(1)
         ws = workspace(x.device)
-        need_grad = any(ctx.needs_input_grad[:3])
         if training:
             work, gen = ws.take(4 * nc)
         else:
@@ -49,7 +48,7 @@ class _StemFn(torch.autograd.Function):
             work = torch.zeros(2 * x.size(1), dtype=torch.float32, device=x.device)
         _ext.note_launch(2)
         dx, dw, db = C.stem_backward(dy, x, code, weight, saved, work)
-        return dx, dw, db, None, None, None, None, None, None
+        return dx, dw, db, None, None, None, None, None, None, None
 
 
 def can_fuse_stem(x, weight, running_mean) -> bool:
@@ -62,10 +61,13 @@ def can_fuse_stem(x, weight, running_mean) -> bool:
 def bn_relu_maxpool(x, weight, bias, running_mean, running_var, training=True, momentum=0.1, eps=1e-5, fused=None,
                     num_batches_tracked=None):
     ok = can_fuse_stem(x, weight, running_mean)
+    need_grad = torch.is_grad_enabled() and (x.requires_grad or (weight is not None and weight.requires_grad))
+    if need_grad and not training:
+        ok = False
     if not (ok if fused is None else (fused and ok)):
         if training and num_batches_tracked is not None:
             num_batches_tracked.add_(1)
         if weight is not None and x.is_cuda and weight.dtype != torch.float32 and x.dtype != weight.dtype:
             weight, bias = weight.to(x.dtype), bias.to(x.dtype)
         return bn_relu_maxpool_reference(x, weight, bias, running_mean, running_var, training, momentum, eps)
-    return _StemFn.apply(x, weight, bias, running_mean, running_var, num_batches_tracked, training, float(momentum), float(eps))
+    return _StemFn.apply(x, weight, bias, running_mean, running_var, num_batches_tracked, training, float(momentum), float(eps), need_grad)
