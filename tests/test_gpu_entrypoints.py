@@ -62,6 +62,12 @@ def test_multiprocessing_entrypoint(tmp_path):
     _finite_losses(out)
 
 
+def test_distributed_entrypoint_cuda_graph_two_gpus(tmp_path):
+    out = _run(_torchrun("distributed.py", 2, COMMON[:6] + ["8"] + COMMON[7:] + ["--cuda-graph", "--lr", "0.01", "--checkpoint-dir", str(tmp_path)], 29805))
+    assert out.count(" * Acc@1") == 2
+    _finite_losses(out)
+
+
 @pytest.mark.parametrize("comm", ["nccl"])
 def test_distributed_entrypoint_library_comm(tmp_path, comm):
     out = _run(_torchrun("distributed.py", 2, COMMON + ["--comm", comm, "--lr", "0.01", "--checkpoint-dir", str(tmp_path)], 29803))
