@@ -412,14 +412,14 @@ static int apply_grid(const Geometry& g) {
 template <typename T>
 static void fwd_impl(const at::Tensor& x, const at::Tensor* res, at::Tensor& y, at::Tensor& mask, at::Tensor& work, at::Tensor& saved,
                      const at::Tensor& w, const at::Tensor& b, at::Tensor& rm, at::Tensor& rv, at::Tensor& nbt, bool training, float momentum,
-                     float eps, bool relu) {
+                     float eps, bool relu, bool stats_ready) {
   const Geometry g = geometry(x);
   cudaStream_t st = at::cuda::getCurrentCUDAStream();
   const T* xp = reinterpret_cast<const T*>(x.data_ptr());
   T* yp = reinterpret_cast<T*>(y.data_ptr());
   const T* rp = res ? reinterpret_cast<const T*>(res->data_ptr()) : nullptr;
   float* wk = work.defined() ? work.data_ptr<float>() : nullptr;
-  if (training) {
+  if (training && !stats_ready) {     // stats_ready: the producing GEMM already reduced sum / sum-of-squares (gemm_bnstats.cu)
     int rpb;
     const int grid = reduce_grid(g, &rpb, resident_ctas(bn_stats_kernel<T>, g.smem));
     bn_stats_kernel<T><<<grid, kBnThreads, g.smem, st>>>(xp, wk, g.M, g.C, rpb);
@@ -444,7 +444,7 @@ static void fwd_impl(const at::Tensor& x, const at::Tensor* res, at::Tensor& y, 
 std::vector<at::Tensor> bn_act_forward(const at::Tensor& x, const c10::optional<at::Tensor>& residual, const at::Tensor& weight,
                                        const at::Tensor& bias, at::Tensor running_mean, at::Tensor running_var,
                                        c10::optional<at::Tensor> num_batches_tracked, bool training, double momentum, double eps, bool relu,
-                                       bool need_mask, at::Tensor work) {
+                                       bool need_mask, at::Tensor work, bool stats_ready) {
   check_nhwc(x, "x");
   TORCH_CHECK(weight.scalar_type() == bias.scalar_type() && weight.is_contiguous() && bias.is_contiguous());
   if (running_mean.defined()) TORCH_CHECK(running_mean.scalar_type() == at::kFloat && running_var.scalar_type() == at::kFloat, "running stats must be fp32");
@@ -469,9 +469,9 @@ std::vector<at::Tensor> bn_act_forward(const at::Tensor& x, const c10::optional<
   }
   if (relu && need_mask) mask = at::empty({x.numel() / 8}, x.options().dtype(at::kByte));
   switch (x.scalar_type()) {
-    case at::kBFloat16: fwd_impl<__nv_bfloat16>(x, res, y, mask, work, saved, weight, bias, running_mean, running_var, nbt, training, (float)momentum, (float)eps, relu); break;
-    case at::kHalf: fwd_impl<__half>(x, res, y, mask, work, saved, weight, bias, running_mean, running_var, nbt, training, (float)momentum, (float)eps, relu); break;
-    case at::kFloat: fwd_impl<float>(x, res, y, mask, work, saved, weight, bias, running_mean, running_var, nbt, training, (float)momentum, (float)eps, relu); break;
+    case at::kBFloat16: fwd_impl<__nv_bfloat16>(x, res, y, mask, work, saved, weight, bias, running_mean, running_var, nbt, training, (float)momentum, (float)eps, relu, stats_ready); break;
+    case at::kHalf: fwd_impl<__half>(x, res, y, mask, work, saved, weight, bias, running_mean, running_var, nbt, training, (float)momentum, (float)eps, relu, stats_ready); break;
+    case at::kFloat: fwd_impl<float>(x, res, y, mask, work, saved, weight, bias, running_mean, running_var, nbt, training, (float)momentum, (float)eps, relu, stats_ready); break;
     default: TORCH_CHECK(false, "unsupported activation dtype");
   }
   return {y, saved, mask};

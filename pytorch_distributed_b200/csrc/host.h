@@ -42,7 +42,7 @@ void amp_update_scale(at::Tensor scale, at::Tensor growth_tracker, at::Tensor fo
 std::vector<at::Tensor> bn_act_forward(const at::Tensor& x, const c10::optional<at::Tensor>& residual, const at::Tensor& weight,
                                        const at::Tensor& bias, at::Tensor running_mean, at::Tensor running_var,
                                        c10::optional<at::Tensor> num_batches_tracked, bool training, double momentum, double eps, bool relu,
-                                       bool need_mask, at::Tensor work);
+                                       bool need_mask, at::Tensor work, bool stats_ready);
 std::vector<at::Tensor> bn_act_backward(const at::Tensor& dy, const at::Tensor& x, const c10::optional<at::Tensor>& mask,
                                         const at::Tensor& weight, const at::Tensor& saved, bool relu, bool has_residual, at::Tensor work);
 
@@ -51,6 +51,9 @@ std::vector<at::Tensor> stem_forward(const at::Tensor& x, const at::Tensor& weig
                                      double eps, bool need_code, at::Tensor work);
 std::vector<at::Tensor> stem_backward(const at::Tensor& dp, const at::Tensor& x, const at::Tensor& code, const at::Tensor& weight,
                                       const at::Tensor& saved, at::Tensor work);
+
+// ---- gemm_bnstats.cu (tcgen05 / TMA / TMEM)
+at::Tensor conv1x1_bnstats(const at::Tensor& x, const at::Tensor& weight, at::Tensor gsum);
 
 // ---- data_ops.cu
 at::Tensor normalize_nhwc(const at::Tensor& src, const at::Tensor& mean, const at::Tensor& std, int64_t out_dtype, bool channels_last);

@@ -15,7 +15,13 @@ import torch
 import torch.nn as nn
 
 from ..ops.bn_act import begin_step, bn_act
+from ..ops.conv_bn import conv1x1_bn_act
 from ..ops.stem import bn_relu_maxpool
+
+# 1x1 conv -> BN pairs run as ONE tcgen05 GEMM with the BN statistics in its epilogue (ops/conv_bn.py); opt-in until the
+# kernel beats cuDNN + bn_stats on every ResNet-50 shape (PTD_FUSED_CONV1X1=1 or models.resnet.FUSED_CONV1X1 = True)
+import os as _os
+FUSED_CONV1X1 = _os.environ.get("PTD_FUSED_CONV1X1", "0") == "1"
 
 
 class BNAct(nn.BatchNorm2d):
@@ -86,9 +92,9 @@ class Bottleneck(nn.Module):
 
     def forward(self, x):
         identity = x if self.downsample is None else self.downsample(x)
-        out = self.bn1(self.conv1(x))
+        out = conv1x1_bn_act(x, self.conv1, self.bn1, enabled=FUSED_CONV1X1)
         out = self.bn2(self.conv2(out))
-        return self.bn3(self.conv3(out), identity)
+        return conv1x1_bn_act(out, self.conv3, self.bn3, identity, enabled=FUSED_CONV1X1)
 
 
 class ResNet(nn.Module):

@@ -68,18 +68,21 @@ def begin_step(device) -> None:
 
 class _BnActFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, residual, weight, bias, running_mean, running_var, nbt, training, momentum, eps, relu, need_grad):
+    def forward(ctx, x, residual, weight, bias, running_mean, running_var, nbt, training, momentum, eps, relu, need_grad, pre=None):
         from .. import _ext
         C = _ext.lib()
         nc = x.size(1)
         ws = workspace(x.device)
-        if training:
+        stats_ready = pre is not None          # (work[4C], generation): sums already reduced by the producing GEMM
+        if stats_ready:
+            work, gen = pre
+        elif training:
             work, gen = ws.take(4 * nc)
         else:
             work, gen = torch.empty(0, dtype=torch.float32, device=x.device), -1
-        _ext.note_launch(2 if training else 1)
+        _ext.note_launch(1 if (stats_ready or not training) else 2)
         y, saved, mask = C.bn_act_forward(x, residual, weight, bias, running_mean, running_var, nbt, training, momentum, eps, relu,
-                                          need_grad, work[: 2 * nc] if training else work)
+                                          need_grad, work[: 2 * nc] if training else work, stats_ready)
         ctx.relu = relu
         ctx.has_res = residual is not None
         ctx.work = work[2 * nc:] if training else None
@@ -101,7 +104,7 @@ class _BnActFn(torch.autograd.Function):
             work = torch.zeros(2 * x.size(1), dtype=torch.float32, device=x.device)   # slice was recycled: use a fresh one
         _ext.note_launch(2)
         dx, dres, dw, db = C.bn_act_backward(dy, x, mask, weight, saved, ctx.relu, ctx.has_res, work)
-        return dx, (dres if ctx.has_res else None), dw, db, None, None, None, None, None, None, None, None
+        return dx, (dres if ctx.has_res else None), dw, db, None, None, None, None, None, None, None, None, None
 
 
 def _can_fuse(x, weight, residual, running_mean=True) -> bool:
