@@ -267,8 +267,9 @@ at::Tensor conv1x1_bnstats(const at::Tensor& x, const at::Tensor& weight, at::Te
   at::Tensor w2 = weight.reshape({N, K}).contiguous();       // [N, K] K-major (a view for both NCHW and NHWC 1x1 weights)
   at::Tensor y = at::empty({x.size(0), N, x.size(2), x.size(3)}, x.options().memory_format(at::MemoryFormat::ChannelsLast));
   const int M = (int)M64;
-  if (N % 256 == 0) launch_gemm<256>(x, w2, y, gsum, M, N, K);
-  else if (N % 128 == 0) launch_gemm<128>(x, w2, y, gsum, M, N, K);
+  static const int max_bn = getenv("PTD_GEMM_BLOCK_N") ? atoi(getenv("PTD_GEMM_BLOCK_N")) : 256;
+  if (N % 256 == 0 && max_bn >= 256) launch_gemm<256>(x, w2, y, gsum, M, N, K);
+  else if (N % 128 == 0 && max_bn >= 128) launch_gemm<128>(x, w2, y, gsum, M, N, K);
   else launch_gemm<64>(x, w2, y, gsum, M, N, K);
   return y;
 }

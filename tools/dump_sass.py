@@ -20,6 +20,9 @@ WANT = {
     "metrics_bf16": r"metrics_kernelI13__nv_bfloat16E",
     "barrier": r"barrier_kernel",
     "fused_sgd_flat_bf16": r"fused_sgd_flat_kernelI13__nv_bfloat16S1_Lb1E",
+    "gemm_bnstats_tcgen05_n256": r"gemm_bnstats_kernelILi256E",
+    "stem_fwd_bf16": r"stem_fwd_kernelI13__nv_bfloat16E",
+    "stem_bwd_apply_bf16": r"stem_bwd_apply_kernelI13__nv_bfloat16E",
     "bn_stats_bf16": r"bn_stats_kernelI13__nv_bfloat16E",
     "bn_apply_bf16_relu_res": r"bn_apply_kernelI13__nv_bfloat16Lb1ELb1E",
     "bn_bwd_reduce_bf16_relu": r"bn_bwd_reduce_kernelI13__nv_bfloat16Lb1E",
@@ -44,7 +47,7 @@ def main():
         cnt = {}
         for o in ops:
             cnt[o] = cnt.get(o, 0) + 1
-        key = [(k, v) for k, v in cnt.items() if re.match(r"(LDGMC|STG\.E\..*SYS|LDG\.E\..*SYS|RED|ATOM|MULTIMEM|ST\.E\..*SYS|LD\.E\..*SYS|MEMBAR|CCTL|NANOSLEEP|BAR)", k)]
+        key = [(k, v) for k, v in cnt.items() if re.match(r"(UTC|UTMA|LDTM|SYNCS|LDGMC|STG\.E\..*SYS|LDG\.E\..*SYS|RED|ATOM|MULTIMEM|ST\.E\..*SYS|LD\.E\..*SYS|MEMBAR|CCTL|NANOSLEEP|BAR)", k)]
         summary.append("%-32s %5d instr; %s" % (name, len(ops), ", ".join("%s x%d" % kv for kv in sorted(key))))
     with open(os.path.join(OUT, "SUMMARY.txt"), "w") as f:
         f.write("SASS evidence (cuobjdump -sass pytorch_distributed_b200/_C.so, sm_100a). LDGMC = multimem.ld_reduce (in-switch reduce),\n"
