@@ -25,7 +25,7 @@ class _Worker:
         if self.world > self.ngpus and args.comm == "auto":
             args.comm = "nccl" if torch.cuda.is_available() else "gloo"
         driver.seed_everything(args)
-        driver.main_worker(gpu, self.world, args, driver.SlurmStrategy() if True else None)
+        driver.main_worker(gpu, self.world, args, driver.SlurmStrategy())
 
 
 def main():

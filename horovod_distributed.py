@@ -26,11 +26,6 @@ def main():
     args.nprocs = launch.default_nprocs(args)
     port = launch.pick_port(launch.DEFAULT_PORT + 1)
     envs = {"MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(port), "WORLD_SIZE": str(args.nprocs)}
-
-    def spawned(i, n, a):
-        os.environ["RANK"] = str(i)
-        worker(i, n, a)
-
     launch.spawn(_HvdSpawn(), args.nprocs, args, extra_env=envs)
 
 

@@ -126,6 +126,12 @@ def bn_act(x, weight, bias, running_mean, running_var, residual: Optional[torch.
             weight, bias = weight.to(x.dtype), bias.to(x.dtype)
         if training and num_batches_tracked is not None:
             num_batches_tracked.add_(1)
+        if not x.is_cuda and x.dtype != torch.float32:
+            # CPU batch_norm wants one dtype for activations and statistics: do the math in fp32 (test / debug path)
+            y = bn_act_reference(x.float(), None if weight is None else weight.float(), None if bias is None else bias.float(),
+                                 running_mean, running_var, None if residual is None else residual.float(), relu, training,
+                                 momentum, eps)
+            return y.to(x.dtype)
         return bn_act_reference(x, weight, bias, running_mean, running_var, residual, relu, training, momentum, eps)
     need_grad = torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad or bias.requires_grad
                                              or (residual is not None and residual.requires_grad))

@@ -69,5 +69,8 @@ def bn_relu_maxpool(x, weight, bias, running_mean, running_var, training=True, m
             num_batches_tracked.add_(1)
         if weight is not None and x.is_cuda and weight.dtype != torch.float32 and x.dtype != weight.dtype:
             weight, bias = weight.to(x.dtype), bias.to(x.dtype)
+        if not x.is_cuda and x.dtype != torch.float32:
+            return bn_relu_maxpool_reference(x.float(), weight.float(), bias.float(), running_mean, running_var, training, momentum,
+                                             eps).to(x.dtype)
         return bn_relu_maxpool_reference(x, weight, bias, running_mean, running_var, training, momentum, eps)
     return _StemFn.apply(x, weight, bias, running_mean, running_var, num_batches_tracked, training, float(momentum), float(eps), need_grad)

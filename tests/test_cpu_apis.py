@@ -1,0 +1,134 @@
+"""CPU tier for the wrapper APIs: hvd shim over gloo, apex namespace, prefetcher, metric pipeline, train step, reduce_mean."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+HVD = r'''
+import os, sys, torch
+sys.path.insert(0, %r)
+import pytorch_distributed_b200.parallel.hvd as hvd
+hvd.init(device="cpu")
+r, n = hvd.rank(), hvd.size()
+assert n == 2 and hvd.local_rank() == r and hvd.is_initialized()
+t = torch.full((5,), float(r + 1))
+out = hvd.allreduce(t, name="barrier")                 # out-of-place, averaged (SURVEY Q4: really returned)
+assert torch.allclose(out, torch.full((5,), 1.5)) and torch.allclose(t, torch.full((5,), float(r + 1)))
+hvd.allreduce_(t, average=False)
+assert torch.allclose(t, torch.full((5,), 3.0))
+h = hvd.allreduce_async_(torch.full((3,), float(r)), average=True)
+assert hvd.poll(h) in (True, False)
+assert torch.allclose(hvd.synchronize(h), torch.full((3,), 0.5))
+m = torch.nn.Sequential(torch.nn.Linear(4, 8), torch.nn.BatchNorm1d(8), torch.nn.Linear(8, 2))
+torch.manual_seed(10 + r)
+for p in m.parameters():
+    torch.nn.init.normal_(p)
+hvd.broadcast_parameters(m.state_dict(), root_rank=0)
+flat = torch.cat([p.detach().reshape(-1) for p in m.parameters()])
+ref = flat.clone(); torch.distributed.broadcast(ref, 0)
+assert torch.equal(flat, ref)
+opt = torch.optim.SGD(m.parameters(), lr=0.1 * (r + 1), momentum=0.9)
+hvd.broadcast_optimizer_state(opt, root_rank=0)
+assert opt.param_groups[0]["lr"] == 0.1
+opt = hvd.DistributedOptimizer(opt, named_parameters=m.named_parameters(), compression=hvd.Compression.fp16)
+assert isinstance(opt, torch.optim.SGD)
+for it in range(3):
+    torch.manual_seed(100 + r + it)
+    x, y = torch.randn(6, 4), torch.randint(0, 2, (6,))
+    opt.zero_grad()
+    torch.nn.functional.cross_entropy(m(x), y).backward()
+    opt.step()
+flat = torch.cat([p.detach().reshape(-1) for p in m.parameters()])
+lo, hi = flat.clone(), flat.clone()
+torch.distributed.all_reduce(lo, op=torch.distributed.ReduceOp.MIN); torch.distributed.all_reduce(hi, op=torch.distributed.ReduceOp.MAX)
+assert torch.allclose(lo, hi, atol=1e-6), (lo - hi).abs().max()      # averaged gradients => identical weights on all ranks
+try:
+    hvd.DistributedOptimizer(torch.optim.SGD(m.parameters(), lr=0.1), named_parameters=[("a", p) for p in m.parameters()])
+    raise SystemExit("duplicate names must be rejected")
+except ValueError:
+    pass
+from pytorch_distributed_b200.utils.dist_ops import reduce_mean
+assert abs(reduce_mean(torch.tensor(float(r)), 2).item() - 0.5) < 1e-6
+print("HVD-OK", r)
+torch.distributed.destroy_process_group()
+'''
+
+
+def test_hvd_api_over_gloo(tmp_path):
+    script = tmp_path / "hvd_check.py"
+    script.write_text(HVD % ROOT)
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29731", str(script)], env=env, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-3000:]
+    assert p.stdout.count("HVD-OK") == 2
+
+
+def test_apex_namespace_surface():
+    from pytorch_distributed_b200 import apex
+    from pytorch_distributed_b200.apex import amp
+    from pytorch_distributed_b200.apex.parallel import DistributedDataParallel, Reducer
+    assert callable(amp.initialize) and callable(amp.scale_loss) and callable(amp.master_params)
+    assert callable(amp.state_dict) and callable(amp.load_state_dict)
+    assert DistributedDataParallel.__name__ == "DistributedDataParallel" and Reducer is not None and apex.amp is amp
+
+
+def test_amp_o2_casts_in_place_and_keeps_fp32_masters_cpu():
+    from pytorch_distributed_b200.models import create_model
+    from pytorch_distributed_b200.ops.fused_sgd import FusedSGD
+    from pytorch_distributed_b200.parallel import amp
+    m = create_model("resnet18", num_classes=4)
+    opt = FusedSGD(m.parameters(), lr=0.1, momentum=0.9)
+    ids = [id(p) for p in m.parameters()]
+    m, opt = amp.initialize(m, opt, opt_level="O2", half_dtype=torch.bfloat16, verbosity=0)
+    assert [id(p) for p in m.parameters()] == ids                      # same Parameter objects: the optimizer stays valid
+    assert all(p.dtype == torch.bfloat16 for p in m.parameters())
+    assert m.bn1.running_mean.dtype == torch.float32
+    x = torch.randn(2, 3, 32, 32)
+    with amp.scale_loss(m(x).float().sum(), opt) as sl:
+        sl.backward()
+    opt.step()
+    masters = list(amp.master_params(opt))
+    assert len(masters) == len(ids) and all(t.dtype == torch.float32 for t in masters)
+    amp._amp_state.enabled = False
+    amp._amp_state.scaler = None
+
+
+def test_prefetcher_cpu_iter_and_next_and_limit():
+    from pytorch_distributed_b200.utils.data import DataPrefetcher, SyntheticLoader, data_prefetcher
+    assert data_prefetcher is DataPrefetcher
+    loader = SyntheticLoader(4, 5, image_size=8, num_classes=3, pin=False)
+    pf = DataPrefetcher(loader, "cpu", dtype=torch.float32, limit=3)
+    got = list(pf)
+    assert len(pf) == 3 and len(got) == 3 and got[0][0].shape == (4, 3, 8, 8) and got[0][1].dtype == torch.int64
+    assert pf.h2d_bytes == 3 * loader.bytes_per_step
+    pf2 = DataPrefetcher(SyntheticLoader(2, 2, image_size=8, pin=False, raw_uint8=True), "cpu", normalize="imagenet255")
+    a, b = pf2.next()
+    assert a.dtype == torch.float32 and abs(float(a.mean())) < 3.0
+    pf2.next()
+    assert pf2.next() == (None, None)
+
+
+def test_metric_pipeline_and_train_step_cpu():
+    from pytorch_distributed_b200 import cli, driver
+    from pytorch_distributed_b200.utils.meters import AverageMeter
+    torch.manual_seed(0)
+    args = cli.parse_args("distributed", ["--device", "cpu", "--synthetic", "-b", "4"])
+    st = driver.Strategy()
+    model = torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(12, 5))
+    st.autocast, st.input_dtype = None, torch.float32
+    meters = (AverageMeter("Loss"), AverageMeter("Acc@1"), AverageMeter("Acc@5"))
+    mp = driver.MetricPipeline(None, torch.device("cpu"), meters, reduce=False)
+    opt = torch.optim.SGD(model.parameters(), lr=0.5)
+    step = driver.TrainStep(st, model, torch.nn.CrossEntropyLoss(), opt, mp, use_graph=True)   # no CUDA => stays eager
+    x, y = torch.randn(4, 3, 2, 2), torch.tensor([0, 1, 2, 3])
+    losses = []
+    for _ in range(20):
+        step(x, y)
+        losses.append(meters[0].val)
+    mp.drain()
+    assert step.graph is None and losses[-1] < losses[0] * 0.5 and meters[2].val == 100.0 and meters[0].count == 80
