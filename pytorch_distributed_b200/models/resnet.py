@@ -18,10 +18,11 @@ from ..ops.bn_act import begin_step, bn_act
 from ..ops.conv_bn import conv1x1_bn_act
 from ..ops.stem import bn_relu_maxpool
 
-# 1x1 conv -> BN pairs run as ONE tcgen05 GEMM with the BN statistics in its epilogue (ops/conv_bn.py); opt-in until the
-# kernel beats cuDNN + bn_stats on every ResNet-50 shape (PTD_FUSED_CONV1X1=1 or models.resnet.FUSED_CONV1X1 = True)
+# 1x1 conv -> BN pairs run as ONE tcgen05 GEMM with the BN statistics in its epilogue (ops/conv_bn.py,
+# profiles/gemm_bnstats_probe.md: -23 % vs cuDNN conv + separate statistics pass over the ResNet-50 shapes).
+# PTD_FUSED_CONV1X1=0 (or models.resnet.FUSED_CONV1X1 = False) restores cuDNN + bn_stats.
 import os as _os
-FUSED_CONV1X1 = _os.environ.get("PTD_FUSED_CONV1X1", "0") == "1"
+FUSED_CONV1X1 = _os.environ.get("PTD_FUSED_CONV1X1", "1") == "1"
 
 
 class BNAct(nn.BatchNorm2d):
@@ -53,6 +54,9 @@ class _Downsample(nn.Sequential):
 
     def __init__(self, cin, cout, stride, fused):
         super().__init__(_conv1x1(cin, cout, stride), BNAct(cout, relu=False, fused=fused))
+
+    def forward(self, x):        # stride-1 projections (layer1) take the tcgen05 GEMM + fused statistics path
+        return conv1x1_bn_act(x, self[0], self[1], enabled=FUSED_CONV1X1)
 
 
 class BasicBlock(nn.Module):

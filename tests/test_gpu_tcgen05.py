@@ -25,12 +25,17 @@ def test_conv1x1_bnstats_matches_fp32_reference(shape):
     ref = F.conv2d(x.float(), w.float())
     assert y.shape == ref.shape and y.is_contiguous(memory_format=torch.channels_last)
     torch.testing.assert_close(y.float(), ref, rtol=1e-2, atol=1e-2 * float(ref.abs().max()))
+    # the statistics are those of the STORED (bf16-rounded) tensor - what a separate BatchNorm pass would reduce
+    yf = y.float()
+    s_own, q_own = yf.sum(dim=(0, 2, 3)), (yf * yf).sum(dim=(0, 2, 3))
+    torch.testing.assert_close(gs[:cout], s_own, rtol=1e-4, atol=1e-4 * float(s_own.abs().max() + 1))
+    torch.testing.assert_close(gs[cout:], q_own, rtol=1e-4, atol=1e-4 * float(q_own.abs().max() + 1))
     s_ref, q_ref = ref.sum(dim=(0, 2, 3)), (ref * ref).sum(dim=(0, 2, 3))
-    torch.testing.assert_close(gs[:cout], s_ref, rtol=1e-3, atol=1e-3 * float(s_ref.abs().max() + 1))
-    torch.testing.assert_close(gs[cout:], q_ref, rtol=1e-3, atol=1e-3 * float(q_ref.abs().max() + 1))
+    torch.testing.assert_close(gs[:cout], s_ref, rtol=1e-2, atol=1e-2 * float(s_ref.abs().max() + 1))
+    torch.testing.assert_close(gs[cout:], q_ref, rtol=1e-2, atol=1e-2 * float(q_ref.abs().max() + 1))
     # accumulates (BN workspace semantics): a second call doubles the sums
     C().conv1x1_bnstats(x, w, gs)
-    torch.testing.assert_close(gs[:cout], 2 * s_ref, rtol=1e-3, atol=2e-3 * float(s_ref.abs().max() + 1))
+    torch.testing.assert_close(gs[:cout], 2 * s_own, rtol=1e-4, atol=2e-4 * float(s_own.abs().max() + 1))
 
 
 def test_bottleneck_with_fused_conv1x1_matches_unfused():

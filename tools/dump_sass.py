@@ -20,7 +20,7 @@ WANT = {
     "metrics_bf16": r"metrics_kernelI13__nv_bfloat16E",
     "barrier": r"barrier_kernel",
     "fused_sgd_flat_bf16": r"fused_sgd_flat_kernelI13__nv_bfloat16S1_Lb1E",
-    "gemm_bnstats_tcgen05_n256": r"gemm_bnstats_kernelILi256E",
+    "gemm_bnstats_tcgen05_n256": r"gemm_bnstats_persistent_kernelILi256E",
     "stem_fwd_bf16": r"stem_fwd_kernelI13__nv_bfloat16E",
     "stem_bwd_apply_bf16": r"stem_bwd_apply_kernelI13__nv_bfloat16E",
     "bn_stats_bf16": r"bn_stats_kernelI13__nv_bfloat16E",
