@@ -448,10 +448,11 @@ static CUtensorMap make_map(const void* ptr, int64_t rows, int64_t cols, int box
 template <int BLOCK_N>
 static void launch_gemm(const at::Tensor& a, const at::Tensor& b, at::Tensor& c, at::Tensor& gsum, int M, int N, int K) {
   constexpr size_t smem = 1024 + kStages * (kBlockM * kBlockK * 2 + BLOCK_N * kBlockK * 2) + 4 * 2 * BLOCK_N * sizeof(float) + 64;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {};                 // the attribute is per device (DataParallel drives several from one process)
+  const int dev = a.get_device();
+  if (!configured[dev & 63]) {
     C10_CUDA_CHECK(cudaFuncSetAttribute(gemm_bnstats_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
+    configured[dev & 63] = true;
   }
   const CUtensorMap ma = make_map(a.data_ptr(), M, K, kBlockM), mb = make_map(b.data_ptr(), N, K, BLOCK_N);
   dim3 grid((M + kBlockM - 1) / kBlockM, N / BLOCK_N);
@@ -463,10 +464,11 @@ static void launch_gemm(const at::Tensor& a, const at::Tensor& b, at::Tensor& c,
 template <int BLOCK_N>
 static void launch_gemm_v2(const at::Tensor& a, const at::Tensor& b, at::Tensor& c, at::Tensor& gsum, int M, int N, int K) {
   constexpr size_t smem = 1024 + kStagesV2 * (kBlockM * kBlockK * 2 + BLOCK_N * kBlockK * 2) + kEpiWarps * 8192 + 4 * 2 * BLOCK_N * sizeof(float) + 128;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {};                 // the attribute is per device (DataParallel drives several from one process)
+  const int dev = a.get_device();
+  if (!configured[dev & 63]) {
     C10_CUDA_CHECK(cudaFuncSetAttribute(gemm_bnstats_persistent_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
+    configured[dev & 63] = true;
   }
   const CUtensorMap ma = make_map(a.data_ptr(), M, K, kBlockM), mb = make_map(b.data_ptr(), N, K, BLOCK_N);
   const CUtensorMap mc = make_store_map(c.data_ptr(), M, N);
