@@ -71,3 +71,18 @@ class Reducer:
     def reduce(self):
         grads = [p.grad for p in self.params if p.grad is not None]
         self.comm.all_reduce_(grads, average=True)
+
+
+def flatten(tensors):
+    """apex_C.flatten: one contiguous 1-D tensor holding the given dense tensors back to back."""
+    return torch.cat([t.contiguous().view(-1) for t in tensors]) if len(tensors) else torch.empty(0)
+
+
+def unflatten(flat, tensors):
+    """apex_C.unflatten: views of ``flat`` shaped like ``tensors``."""
+    out, off = [], 0
+    for t in tensors:
+        n = t.numel()
+        out.append(flat.narrow(0, off, n).view_as(t))
+        off += n
+    return out

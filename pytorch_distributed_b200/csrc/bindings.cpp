@@ -89,6 +89,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("found_inf"), py::arg("nesterov"), py::arg("first_step"));
   m.def("fused_sgd_multi", &fused_sgd_multi);
   m.def("multi_tensor_scale", &multi_tensor_scale);
+  m.def("multi_tensor_axpby", &multi_tensor_axpby);
   m.def("amp_update_scale", &amp_update_scale);
   m.def("bn_act_forward", &bn_act_forward);
   m.def("bn_act_backward", &bn_act_backward);

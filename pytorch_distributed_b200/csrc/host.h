@@ -35,6 +35,8 @@ void fused_sgd_multi(std::vector<at::Tensor> grads, std::vector<at::Tensor> para
                      std::vector<at::Tensor> model_copies, at::Tensor hyper, c10::optional<at::Tensor> found_inf, bool nesterov,
                      bool first_step);
 void multi_tensor_scale(std::vector<at::Tensor> src, std::vector<at::Tensor> dst, double scale, at::Tensor found_inf);
+void multi_tensor_axpby(std::vector<at::Tensor> x, std::vector<at::Tensor> y, std::vector<at::Tensor> out, double a, double b,
+                        at::Tensor found_inf);
 void amp_update_scale(at::Tensor scale, at::Tensor growth_tracker, at::Tensor found_inf, double growth, double backoff,
                       int64_t interval, at::Tensor hyper);
 

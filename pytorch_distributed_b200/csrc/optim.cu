@@ -163,6 +163,20 @@ __global__ void __launch_bounds__(256) multi_tensor_scale_kernel(const __grid_co
   if (__syncthreads_or(bad) && threadIdx.x == 0) *found_inf = 1;
 }
 
+// out = a * x + b * y, found_inf |= any non-finite(x or y)   (apex amp_C.multi_tensor_axpby: master-gradient accumulation)
+__global__ void __launch_bounds__(256) multi_tensor_axpby_kernel(const __grid_constant__ MtaArgs<3> a, float ca, float cb, int* found_inf) {
+  const int t = a.block_tensor[blockIdx.x];
+  const int64_t begin = (int64_t)a.block_chunk[blockIdx.x] * kMtaChunk;
+  const int64_t end = min(begin + (int64_t)kMtaChunk, a.numel[t]);
+  bool bad = false;
+  for (int64_t i = begin + threadIdx.x; i < end; i += blockDim.x) {
+    const float x = ld_any(a.ptr[0][t], a.dtype[0][t], i), y = ld_any(a.ptr[1][t], a.dtype[1][t], i);
+    bad |= !isfinite(x) || !isfinite(y);
+    st_any(a.ptr[2][t], a.dtype[2][t], i, ca * x + cb * y);
+  }
+  if (__syncthreads_or(bad) && threadIdx.x == 0) *found_inf = 1;
+}
+
 static uint8_t dtype_code(const at::Tensor& t) {
   switch (t.scalar_type()) {
     case at::kFloat: return kF32;
@@ -235,6 +249,19 @@ void multi_tensor_scale(std::vector<at::Tensor> src, std::vector<at::Tensor> dst
   cudaStream_t st = at::cuda::getCurrentCUDAStream();
   mta_for_each<2>({src, dst}, [&](const MtaArgs<2>& a, int nb) {
     multi_tensor_scale_kernel<<<nb, 256, 0, st>>>(a, (float)scale, found_inf.data_ptr<int>());
+    C10_CUDA_KERNEL_LAUNCH_CHECK();
+  });
+}
+
+void multi_tensor_axpby(std::vector<at::Tensor> x, std::vector<at::Tensor> y, std::vector<at::Tensor> out, double a, double b,
+                        at::Tensor found_inf) {
+  if (x.empty()) return;
+  TORCH_CHECK(x.size() == y.size() && x.size() == out.size());
+  TORCH_CHECK(found_inf.scalar_type() == at::kInt && found_inf.numel() >= 1);
+  c10::cuda::CUDAGuard guard(x[0].device());
+  cudaStream_t st = at::cuda::getCurrentCUDAStream();
+  mta_for_each<3>({x, y, out}, [&](const MtaArgs<3>& args, int nb) {
+    multi_tensor_axpby_kernel<<<nb, 256, 0, st>>>(args, (float)a, (float)b, found_inf.data_ptr<int>());
     C10_CUDA_KERNEL_LAUNCH_CHECK();
   });
 }

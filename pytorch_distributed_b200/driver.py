@@ -33,6 +33,8 @@ from .utils.data import DataPrefetcher, build_loaders
 from .utils.meters import AverageMeter, ProgressMeter, accuracy, adjust_learning_rate
 
 _DTYPES = {"fp32": torch.float32, "bf16": torch.bfloat16, "fp16": torch.float16}
+_NVTX = os.environ.get("PTD_NVTX", "0") == "1"
+_POISON = os.environ.get("PTD_DEBUG_POISON", "0") == "1"
 
 
 def seed_everything(args) -> None:
@@ -174,6 +176,9 @@ class TrainStep:
         self.static_x = self.static_y = self.static_m = None
 
     def _body(self, images, target, dev=None):
+        nvtx = _NVTX and images.is_cuda          # PTD_NVTX=1: forward / backward(+bucket all-reduce) / optimizer ranges for nsys / ncu
+        if nvtx:
+            torch.cuda.nvtx.range_push("ptd.forward")
         output = self.st.forward(self.model, images)
         loss = self.criterion(output.float() if output.dtype != torch.float32 else output, target)
         if dev is None:
@@ -182,8 +187,19 @@ class TrainStep:
             self.metrics.launch(output, target, loss, dev)
         if dev is None:
             self.optimizer.zero_grad()
+        if nvtx:
+            torch.cuda.nvtx.range_pop()
+            torch.cuda.nvtx.range_push("ptd.backward")
         self.st.backward(loss, self.optimizer)
+        if nvtx:
+            torch.cuda.nvtx.range_pop()
+            torch.cuda.nvtx.range_push("ptd.optimizer")
         self.optimizer.step()
+        if nvtx:
+            torch.cuda.nvtx.range_pop()
+        eng = getattr(self.st, "engine", None)
+        if _POISON and eng is not None and getattr(eng, "_flat", None) is not None and getattr(eng, "fused", False):
+            eng.grad_arena().fill_(float("nan"))   # PTD_DEBUG_POISON=1: a stale read of the wire arena shows up as NaN
 
     def _capture(self, images, target):
         self.static_x, self.static_y = images.clone(), target.clone()
