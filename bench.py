@@ -47,7 +47,7 @@ def parse():
     p.add_argument("--optimizer", default="fused")
     p.add_argument("--skip-e2e", action="store_true")
     p.add_argument("--no-cuda-graph", action="store_true")
-    p.add_argument("--entry", default="distributed", choices=["distributed", "apex_distributed", "horovod_distributed"])
+    p.add_argument("--entry", default="distributed", choices=["distributed", "apex_distributed", "horovod_distributed", "dataparallel"])
     p.add_argument("--opt-level", default="O2")
     return p.parse_args()
 
@@ -171,11 +171,14 @@ def run_own(a):
     from pytorch_distributed_b200.utils.meters import AverageMeter
 
     rank, local_rank, world = dist_env()
+    dp = a.entry == "dataparallel"          # one process drives a.gpus devices (BASELINE config 5)
     assert world == a.gpus or world == 1, "launch with torchrun --nproc-per-node %d" % a.gpus
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
-    argv = ["-a", a.arch, "-b", str(a.batch_per_gpu * world), "--synthetic", "--precision", a.precision, "--comm", a.comm,
+    argv = ["-a", a.arch, "-b", str(a.batch_per_gpu * (a.gpus if dp else world)), "--synthetic", "--precision", a.precision, "--comm", a.comm,
             "--optimizer", a.optimizer, "--quiet"]
+    if dp:
+        argv += ["--gpus", ",".join(str(i) for i in range(a.gpus))]
     if a.no_fused_bn:
         argv.append("--no-fused-bn")
     if a.entry == "apex_distributed":
@@ -190,7 +193,7 @@ def run_own(a):
     model, optimizer = st.build(model, args, device, local_rank)
     criterion = torch.nn.CrossEntropyLoss().to(device)
     torch.backends.cudnn.benchmark = True
-    B = a.batch_per_gpu
+    B = a.batch_per_gpu * (a.gpus if dp else 1)
     W, K = a.warmup, a.steps
     losses, top1, top5 = AverageMeter("Loss"), AverageMeter("Acc@1"), AverageMeter("Acc@5")
     metrics = driver.MetricPipeline(getattr(st, "comm", None), device, (losses, top1, top5), reduce=True)
@@ -264,11 +267,11 @@ def run_own(a):
     if rank == 0:
         base = published_baseline()
         out = {
-            "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
+            "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": a.gpus if dp else world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": (value / base) if base else None, "dtype": args.precision, "data": "synthetic",
             "config": {"model": a.arch, "global_batch": B * world, "seq_len": None, "image_size": args.image_size,
-                       "parallelism": "dp%d" % world, "entry": a.entry, "comm": getattr(comm, "backend", "none"),
+                       "parallelism": "dp%d" % (a.gpus if dp else world), "entry": a.entry, "comm": getattr(comm, "backend", "none"),
                        "nvls": bool(getattr(comm, "nvls", False)), "channels_last": bool(args.channels_last),
                        "fused_bn": args.fused_bn is not False, "optimizer": a.optimizer, "cuda_graph": step.graph is not None,
                        "l2_policy": "inputs larger than L2 (4 x 38.5 MB bf16 batches + GBs of activations per step)"},
