@@ -66,7 +66,7 @@ class Plan:
 class FusedCommunicator:
     backend = "fused"
 
-    def __init__(self, group=None, device: Optional[torch.device] = None, arena_bytes: int = 512 << 20, timeout_ms: int = 30000,
+    def __init__(self, group=None, device: Optional[torch.device] = None, arena_bytes: Optional[int] = None, timeout_ms: int = 120000,
                  allow_nvls: Optional[bool] = None, max_ctas: int = 32):
         from .. import _ext
         self._C = _ext.lib()
@@ -77,6 +77,9 @@ class FusedCommunicator:
         if self.world > self._C.MAX_WORLD:
             raise RuntimeError("world size %d exceeds the fused communicator limit %d" % (self.world, self._C.MAX_WORLD))
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        if arena_bytes is None:       # 1 GiB covers ResNet-152-sized models (gradient arena + double-buffered fp32 weight broadcast)
+            arena_bytes = int(os.environ.get("PTD_ARENA_MB", "1024")) << 20
+        timeout_ms = int(os.environ.get("PTD_COMM_TIMEOUT_MS", timeout_ms))
         self.max_blocks = self._C.MAX_BLOCKS
         self.max_ctas = min(max_ctas, self.max_blocks)
         self.header_bytes = P.round_up(self._C.SIGNAL_PAD_BYTES, 128 << 10)
