@@ -463,7 +463,7 @@ def main_worker(local_rank: int, nprocs: int, args, strategy: Optional[Strategy]
     train_loader, val_loader, train_sampler, val_sampler = build_loaders(args, args.batch_size, distributed=st.distributed,
                                                                         raw_uint8=st.raw_uint8_loader)
     if args.resume:
-        ck = load_checkpoint(args.resume, st.unwrapped(model), optimizer)
+        ck = load_checkpoint(args.resume, st.unwrapped(model), optimizer, engine=getattr(st, "engine", None))
         args.start_epoch = ck.get("epoch", args.start_epoch)
         best_acc1 = float(ck.get("best_acc1", 0.0))
         print("=> loaded checkpoint '{}' (epoch {})".format(args.resume, args.start_epoch))

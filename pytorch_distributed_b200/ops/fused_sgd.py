@@ -163,3 +163,24 @@ class FusedSGD(Optimizer):
 
     def zero_grad(self, set_to_none: bool = True):
         super().zero_grad(set_to_none=set_to_none)
+
+    def load_state_dict(self, state_dict):
+        """Standard ``Optimizer.load_state_dict``; in flat mode the loaded momentum is copied INTO the flat buffer
+        (the kernel reads that buffer, not the per-parameter tensors) and the state entries are re-pointed at its views."""
+        super().load_state_dict(state_dict)
+        loaded = False
+        if self._flat is not None:
+            eng = self._flat.engine
+            with torch.no_grad():
+                for i, p in enumerate(eng.params):
+                    buf = self.state.get(p, {}).get("momentum_buffer")
+                    off, cnt = eng.param_elem_off[i], p.numel()
+                    view = self._flat.momentum[off:off + cnt].as_strided(p.size(), p.stride())
+                    if buf is not None and buf.data_ptr() != view.data_ptr():
+                        view.copy_(buf.to(view.dtype))
+                        loaded = True
+                    self.state[p]["momentum_buffer"] = view
+        else:
+            loaded = any("momentum_buffer" in st for st in self.state.values())
+        if loaded:
+            self._steps = max(self._steps, 1)      # do not re-initialise the momentum on the next step

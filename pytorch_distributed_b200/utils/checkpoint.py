@@ -44,7 +44,7 @@ def save_checkpoint(state, is_best: bool, filename: str = "checkpoint.pth.tar", 
     return path
 
 
-def load_checkpoint(path: str, module: torch.nn.Module, optimizer=None, map_location="cpu"):
+def load_checkpoint(path: str, module: torch.nn.Module, optimizer=None, map_location="cpu", engine=None):
     ckpt = torch.load(path, map_location=map_location, weights_only=False)
     sd = ckpt["state_dict"]
     if all(k.startswith("module.") for k in sd):
@@ -54,6 +54,14 @@ def load_checkpoint(path: str, module: torch.nn.Module, optimizer=None, map_loca
         for k, v in sd.items():
             if k in own:
                 own[k].copy_(v.to(own[k].dtype))
+        # low-precision model copies are derived from fp32 master weights: the masters must get the checkpoint too,
+        # otherwise the next optimizer step would regenerate the model from stale masters
+        if engine is not None and hasattr(engine, "master_params"):
+            idx = {id(p): i for i, p in enumerate(engine.params)}
+            masters = engine.master_params()
+            for name, p in module.named_parameters():
+                if id(p) in idx and name in sd:
+                    masters[idx[id(p)]].copy_(sd[name].to(device=masters[idx[id(p)]].device, dtype=torch.float32))
     if optimizer is not None and "optimizer" in ckpt:
         try:
             optimizer.load_state_dict(ckpt["optimizer"])
