@@ -13,6 +13,7 @@ hidden in the DDP constructor (:147).
 from __future__ import annotations
 
 import os
+import threading
 import uuid
 from typing import List, Optional, Sequence
 
@@ -86,6 +87,7 @@ class FusedCommunicator:
         self._bump = self.header_bytes
         self._next_channel = 0
         self._plans = {}
+        self._lock = threading.RLock()      # plans / arena offsets may be requested from the hvd dispatcher thread too
         if allow_nvls is None:
             allow_nvls = os.environ.get("PTD_NVLS", "1") != "0"
         self.symm_backend = "native"
@@ -197,12 +199,13 @@ class FusedCommunicator:
 
     # ------------------------------------------------------------------ resources
     def alloc(self, nbytes: int, align: int = 4096) -> int:
-        off = P.round_up(self._bump, align)
-        if off + nbytes > self.arena.bytes:
-            raise RuntimeError("symmetric arena exhausted: need %d more bytes (capacity %d); raise arena_bytes" %
-                               (off + nbytes - self.arena.bytes, self.arena.bytes))
-        self._bump = off + nbytes
-        return off
+        with self._lock:
+            off = P.round_up(self._bump, align)
+            if off + nbytes > self.arena.bytes:
+                raise RuntimeError("symmetric arena exhausted: need %d more bytes (capacity %d); raise PTD_ARENA_MB / arena_bytes" %
+                                   (off + nbytes - self.arena.bytes, self.arena.bytes))
+            self._bump = off + nbytes
+            return off
 
     def new_channel(self) -> int:
         ch = self._next_channel
@@ -233,11 +236,12 @@ class FusedCommunicator:
                                int(root))
 
     def _cached_plan(self, key, tensors, wire, double_buffer, max_ctas=None):
-        pl = self._plans.get(key)
-        if pl is None:
-            pl = self.make_plan([t.numel() for t in tensors], wire, max_ctas=max_ctas, double_buffer=double_buffer)
-            self._plans[key] = pl
-        return pl
+        with self._lock:
+            pl = self._plans.get(key)
+            if pl is None:
+                pl = self.make_plan([t.numel() for t in tensors], wire, max_ctas=max_ctas, double_buffer=double_buffer)
+                self._plans[key] = pl
+            return pl
 
     @staticmethod
     def _sig(tensors):
