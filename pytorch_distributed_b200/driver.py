@@ -526,7 +526,8 @@ def train(train_loader, model, criterion, optimizer, epoch, st: Strategy, device
     model.train()
     step = getattr(st, "_train_step", None)
     if step is None or step.model is not model:
-        step = st._train_step = TrainStep(st, model, criterion, optimizer, metrics, use_graph=args.cuda_graph and st.graph_capable)
+        fused = getattr(getattr(st, "comm", None), "backend", "") == "fused"     # library collectives are not captured
+        step = st._train_step = TrainStep(st, model, criterion, optimizer, metrics, use_graph=args.cuda_graph and st.graph_capable and fused)
     step.metrics = metrics
     end = time.time()
     t0 = end
