@@ -464,6 +464,8 @@ def main_worker(local_rank: int, nprocs: int, args, strategy: Optional[Strategy]
                                                                         raw_uint8=st.raw_uint8_loader)
     if args.resume:
         ck = load_checkpoint(args.resume, st.unwrapped(model), optimizer, engine=getattr(st, "engine", None))
+        if ck.get("amp") and hasattr(st, "amp"):
+            st.amp.load_state_dict(ck["amp"])
         args.start_epoch = ck.get("epoch", args.start_epoch)
         best_acc1 = float(ck.get("best_acc1", 0.0))
         print("=> loaded checkpoint '{}' (epoch {})".format(args.resume, args.start_epoch))
@@ -492,6 +494,7 @@ def main_worker(local_rank: int, nprocs: int, args, strategy: Optional[Strategy]
                 "state_dict": export_state_dict(st.unwrapped(model), getattr(st, "engine", None)),
                 "best_acc1": best_acc1,
                 "optimizer": optimizer.state_dict() if args.resume or os.environ.get("PTD_SAVE_OPTIMIZER") else None,
+                "amp": st.amp.state_dict() if hasattr(st, "amp") else None,      # loss-scaler state (apex entrypoint)
             }, is_best, directory=args.checkpoint_dir)
     _shutdown(st)
 

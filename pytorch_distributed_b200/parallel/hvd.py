@@ -276,16 +276,17 @@ class _FusionEngine:
                 self.params[i].grad = g
             grads.append(g)
         if self.fused:
-            key = tuple(ids)
-            plan = self._plans.get(key)
             wire = self.wire or ("fp32" if grads[0].dtype == torch.float32 else ("bf16" if grads[0].dtype == torch.bfloat16 else "fp16"))
-            if plan is None:
-                plan = self.comm.make_plan([g.numel() for g in grads], wire)
-                self._plans[key] = plan
             if evs[-1] is not None:
                 self.stream.wait_event(evs[-1])     # events are stream-ordered: the last one covers the group
-            with torch.cuda.stream(self.stream):
-                self.comm.run(plan, grads, KIND_TWO_SHOT, self.channel, scale=1.0 / self.comm.world, writeback=True)
+            for lo in range(0, len(ids), 256):      # one kernel launch carries at most 256 tensor pointers
+                sub_ids, sub = tuple(ids[lo:lo + 256]), grads[lo:lo + 256]
+                plan = self._plans.get(sub_ids)     # response cache: the same fusion group recurs every step
+                if plan is None:
+                    plan = self.comm.make_plan([g.numel() for g in sub], wire)
+                    self._plans[sub_ids] = plan
+                with torch.cuda.stream(self.stream):
+                    self.comm.run(plan, sub, KIND_TWO_SHOT, self.channel, scale=1.0 / self.comm.world, writeback=True)
         else:
             self.comm.all_reduce_(grads, average=True, wire=self.wire)
 
