@@ -41,4 +41,9 @@ def create_model(arch: str, pretrained: bool = False, num_classes: int = 1000, f
         return tvm.__dict__[arch](pretrained=True)
     print("=> creating model '{}'".format(arch))
     kwargs = {} if num_classes == 1000 else {"num_classes": num_classes}
-    return tvm.__dict__[arch](**kwargs)
+    model = tvm.__dict__[arch](**kwargs)
+    if fused_bn:                       # explicit --fused-bn: rewrite Sequential BN -> ReLU pairs of zoo models (models/surgery.py)
+        from .surgery import fuse_bn_relu
+        n = fuse_bn_relu(model)
+        print("=> fused %d BatchNorm+ReLU pairs of '%s'" % (n, arch))
+    return model
