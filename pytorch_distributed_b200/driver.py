@@ -325,8 +325,9 @@ class Strategy:
         return model.module if hasattr(model, "module") else model
 
     def prefetcher(self, loader, device, args, limit=None):
+        raw = self.raw_uint8_loader or getattr(loader, "raw_uint8", False)     # native shard loader ships uint8 pixels
         return DataPrefetcher(loader, device, dtype=self.input_dtype, channels_last=bool(args.channels_last),
-                              normalize="imagenet255" if self.raw_uint8_loader else None, limit=limit)
+                              normalize="imagenet255" if raw else None, limit=limit)
 
 
 class ApexStrategy(Strategy):

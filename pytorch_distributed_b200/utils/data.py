@@ -71,6 +71,10 @@ def _world():
 def build_loaders(args, batch_size: int, distributed: bool = True, raw_uint8: bool = False):
     """(train_loader, val_loader, train_sampler, val_sampler) for this rank.  ``batch_size`` is per loader."""
     rank, world = _world() if distributed else (0, 1)
+    if args.data and not args.synthetic:
+        from . import shards
+        if shards.find_shards(args.data, "train"):          # pre-decoded shards -> native C++ loader (always uint8 batches)
+            return shards.build_shard_loaders(args, batch_size, rank, world)
     use_synth = args.synthetic or not args.data or not os.path.isdir(os.path.join(args.data, "train"))
     if use_synth:
         shards = world if distributed else 1
@@ -168,6 +172,10 @@ class DataPrefetcher:
         with torch.cuda.stream(self.stream):
             img = img.to(self.device, non_blocking=True)
             tgt = tgt.to(self.device, non_blocking=True)
+            if hasattr(self.loader, "batch_copied"):         # ring-buffer loaders recycle the pinned slot after this event
+                ev = torch.cuda.Event()
+                ev.record(self.stream)
+                self.loader.batch_copied(ev)
             img = self._convert(img)
         return img, tgt
 
