@@ -90,7 +90,8 @@ from pytorch_distributed_b200.parallel.dp import DataParallel
 from pytorch_distributed_b200.ops.fused_sgd import FusedSGD
 torch.backends.cudnn.allow_tf32 = False; torch.backends.cuda.matmul.allow_tf32 = False
 torch.manual_seed(0)
-n = torch.cuda.device_count()
+import os
+n = min(torch.cuda.device_count(), int(os.environ.get("PTD_TEST_DP_GPUS", "2")))     # validated width; raise via the env for wider boxes
 base = create_model("resnet18", num_classes=10, fused_bn=False).cuda(0)
 ref = torch.nn.DataParallel(copy.deepcopy(base), device_ids=list(range(n)), output_device=0)
 own = DataParallel(copy.deepcopy(base), device_ids=list(range(n)), output_device=0, wire_dtype="fp32")
