@@ -100,8 +100,10 @@ def build_loaders(args, batch_size: int, distributed: bool = True, raw_uint8: bo
     else:
         ts, vs = None, None
     pin = torch.cuda.is_available()
+    # a captured step replays one batch shape: under --cuda-graph the ragged last training batch is dropped (validation is eager)
     train = torch.utils.data.DataLoader(train_ds, batch_size=batch_size, shuffle=(ts is None), num_workers=args.workers,
-                                        pin_memory=pin, sampler=ts, persistent_workers=args.workers > 0)
+                                        pin_memory=pin, sampler=ts, persistent_workers=args.workers > 0,
+                                        drop_last=bool(getattr(args, "cuda_graph", False)) and len(train_ds) >= batch_size * max(1, world))
     val = torch.utils.data.DataLoader(val_ds, batch_size=batch_size, shuffle=False, num_workers=args.workers, pin_memory=pin,
                                       sampler=vs, persistent_workers=args.workers > 0)
     return train, val, ts or _EpochSampler(), vs or _EpochSampler()

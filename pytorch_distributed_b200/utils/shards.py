@@ -237,6 +237,11 @@ def build_shard_loaders(args, batch_size: int, rank: int, world: int):
         raise FileNotFoundError("no train-*.ptds / val-*.ptds under %r (tools/make_shards.py writes them)" % (args.data,))
     seed = args.seed or 0
     workers = max(1, args.workers)
-    train = ShardLoader(train_paths, batch_size, args.image_size, train=True, seed=seed, rank=rank, world=world, workers=workers)
+    # a captured step replays one batch shape: under --cuda-graph the ragged last training batch is dropped (validation is eager)
+    drop = bool(getattr(args, "cuda_graph", False))
+    train = ShardLoader(train_paths, batch_size, args.image_size, train=True, seed=seed, rank=rank, world=world, workers=workers,
+                        drop_last=drop)
+    if drop and len(train) == 0:          # fewer samples than one batch: keep them
+        train = ShardLoader(train_paths, batch_size, args.image_size, train=True, seed=seed, rank=rank, world=world, workers=workers)
     val = ShardLoader(val_paths, batch_size, args.image_size, train=False, seed=seed, rank=rank, world=world, workers=workers)
     return train, val, train.sampler, val.sampler

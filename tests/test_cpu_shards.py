@@ -125,6 +125,13 @@ def test_sampler_covers_dataset_once_per_epoch(tmp_path):
     assert [i for _ in ld for i in ld.last_ids.tolist()] == orders[1]
 
 
+def test_drop_last_gives_full_batches_only(tmp_path):
+    paths, _ = _write(tmp_path, n=37)
+    ld = shards.ShardLoader(paths, 8, 16, train=True, seed=7, rank=1, world=2, workers=2, pin=False, drop_last=True)
+    sizes = [x.shape[0] for x, _ in ld]
+    assert sizes == [8, 8] and len(ld) == 2               # 37 // 2 = 18 samples -> two full batches
+
+
 def test_batches_do_not_depend_on_thread_count(tmp_path):
     paths, _ = _write(tmp_path, n=23)
     outs = []
