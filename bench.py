@@ -302,8 +302,22 @@ def run_reference(a):
     run(a, METRIC, ClockSampler, published_baseline)
 
 
+def _self_launch(a) -> None:
+    """``python bench.py --gpus N`` without a launcher: re-run under torchrun (one rank per GPU) and pass its exit code on."""
+    import socket
+    import subprocess
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(a.gpus), "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
+    sys.exit(subprocess.call(cmd))
+
+
 if __name__ == "__main__":
     a = parse()
+    if a.gpus > 1 and "RANK" not in os.environ and not (a.impl == "own" and a.entry == "dataparallel"):
+        _self_launch(a)
     if a.impl == "reference":
         run_reference(a)
     else:
