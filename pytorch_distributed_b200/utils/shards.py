@@ -90,14 +90,17 @@ def find_shards(data_dir: str, split: str) -> List[str]:
 def _decode(job):
     path, label, max_side = job
     from PIL import Image
-    with Image.open(path) as im:
-        im = im.convert("RGB")
-        w, h = im.size
-        short = min(w, h)
-        if max_side and short > max_side:            # keep the aspect ratio: RandomResizedCrop still sees the whole image
-            s = max_side / short
-            im = im.resize((max(1, round(w * s)), max(1, round(h * s))), Image.BILINEAR)
-        return np.asarray(im, dtype=np.uint8), label
+    try:
+        with Image.open(path) as im:
+            im = im.convert("RGB")                       # grey-scale / CMYK / palette files of ImageNet included
+            w, h = im.size
+            short = min(w, h)
+            if max_side and short > max_side:            # keep the aspect ratio: RandomResizedCrop still sees the whole image
+                s = max_side / short
+                im = im.resize((max(1, round(w * s)), max(1, round(h * s))), Image.BILINEAR)
+            return np.asarray(im, dtype=np.uint8), label
+    except Exception as e:                               # unreadable file: reported and skipped, like a filtered sample
+        return None, "%s: %s" % (path, e)
 
 
 def write_shards(split_dir: str, out_dir: str, split: str, max_side: int = 256, per_shard: int = 4096, workers: int = 0,
@@ -120,6 +123,9 @@ def write_shards(split_dir: str, out_dir: str, split: str, max_side: int = 256, 
         stream = map(_decode, jobs)
     try:
         for i, (arr, label) in enumerate(stream):
+            if arr is None:
+                (log or print)("skipped unreadable image %s" % (label,))
+                continue
             if writer is None or writer.full:
                 if writer is not None:
                     writer.close()

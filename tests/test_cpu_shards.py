@@ -185,6 +185,20 @@ def test_prefetcher_normalises_shard_batches(tmp_path):
     assert torch.allclose(got, (raw / 255.0 - mean) / std, atol=1e-5)
 
 
+def test_writer_skips_unreadable_and_converts_modes(tmp_path):
+    from PIL import Image
+    d = tmp_path / "raw" / "train" / "a"
+    d.mkdir(parents=True)
+    Image.fromarray(np.full((20, 30), 77, dtype=np.uint8), mode="L").save(str(d / "grey.png"))
+    Image.fromarray(np.zeros((12, 12, 3), dtype=np.uint8)).save(str(d / "rgb.png"))
+    (d / "broken.png").write_bytes(b"not an image")
+    msgs = []
+    paths = shards.write_shards(str(tmp_path / "raw" / "train"), str(tmp_path / "out"), "train", max_side=16, log=msgs.append)
+    idx = shards.read_index(paths[0])
+    assert len(idx) == 2 and any("broken.png" in m for m in msgs)
+    assert sorted((e[1], e[2]) for e in idx) == [(12, 12), (16, 24)]          # grey 20x30 -> RGB, short side capped at 16
+
+
 def test_entrypoint_trains_from_shards(tmp_path):
     """ImageFolder -> tools/make_shards.py -> distributed.py --data <shards> under torchrun (gloo, world 2)."""
     from PIL import Image
