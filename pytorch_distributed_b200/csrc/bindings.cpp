@@ -93,6 +93,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("amp_update_scale", &amp_update_scale);
   m.def("bn_act_forward", &bn_act_forward);
   m.def("bn_act_backward", &bn_act_backward);
+  m.def("bn_act_backward2", &bn_act_backward2);
   m.def("stem_forward", &stem_forward);
   m.def("stem_backward", &stem_backward);
   m.def("conv1x1_bnstats", &conv1x1_bnstats);

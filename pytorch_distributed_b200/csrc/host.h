@@ -47,6 +47,9 @@ std::vector<at::Tensor> bn_act_forward(const at::Tensor& x, const c10::optional<
                                        bool need_mask, at::Tensor work, bool stats_ready);
 std::vector<at::Tensor> bn_act_backward(const at::Tensor& dy, const at::Tensor& x, const c10::optional<at::Tensor>& mask,
                                         const at::Tensor& weight, const at::Tensor& saved, bool relu, bool has_residual, at::Tensor work);
+std::vector<at::Tensor> bn_act_backward2(const at::Tensor& dy_a, const at::Tensor& dy_b, const at::Tensor& x,
+                                         const c10::optional<at::Tensor>& mask, const at::Tensor& weight, const at::Tensor& saved, bool relu,
+                                         at::Tensor work);
 
 std::vector<at::Tensor> stem_forward(const at::Tensor& x, const at::Tensor& weight, const at::Tensor& bias, at::Tensor running_mean,
                                      at::Tensor running_var, c10::optional<at::Tensor> num_batches_tracked, bool training, double momentum,

@@ -23,6 +23,16 @@ from ..ops.stem import bn_relu_maxpool
 # PTD_FUSED_CONV1X1=0 (or models.resnet.FUSED_CONV1X1 = False) restores cuDNN + bn_stats.
 import os as _os
 FUSED_CONV1X1 = _os.environ.get("PTD_FUSED_CONV1X1", "1") == "1"
+# A block's output has two consumers (the next block's first conv and its skip connection).  With SPLIT_RESGRAD the last
+# BNAct of a block hands out two aliases of its output, so the two gradients reach its backward separately and are
+# summed inside the BN-backward reduction pass (csrc/bn_act.cu: bn_act_backward2) instead of by an autograd add:
+# 7 instead of 9 tensor passes over the widest activations.  Opt-in until it has been timed on hardware.
+SPLIT_RESGRAD = _os.environ.get("PTD_SPLIT_RESGRAD", "0") == "1"
+
+
+def _pair(x):
+    """(input of the main path, input of the skip path) - the same tensor unless the producer split its output."""
+    return x if isinstance(x, tuple) else (x, x)
 
 
 class BNAct(nn.BatchNorm2d):
@@ -33,12 +43,12 @@ class BNAct(nn.BatchNorm2d):
         self.relu = relu
         self.fused = fused
 
-    def forward(self, x, residual=None):  # type: ignore[override]
+    def forward(self, x, residual=None, split=False):  # type: ignore[override]
         training = self.training or not self.track_running_stats
         nbt = self.num_batches_tracked if (self.training and self.track_running_stats) else None   # bumped inside the kernel
         return bn_act(x, self.weight, self.bias, self.running_mean, self.running_var, residual=residual, relu=self.relu,
                       training=training, momentum=0.1 if self.momentum is None else self.momentum, eps=self.eps, fused=self.fused,
-                      num_batches_tracked=nbt)
+                      num_batches_tracked=nbt, split=split)
 
 
 def _conv3x3(cin, cout, stride=1, groups=1, dilation=1):
@@ -74,9 +84,10 @@ class BasicBlock(nn.Module):
         self.stride = stride
 
     def forward(self, x):
-        identity = x if self.downsample is None else self.downsample(x)
+        x, skip = _pair(x)
+        identity = skip if self.downsample is None else self.downsample(skip)
         out = self.bn1(self.conv1(x))
-        return self.bn2(self.conv2(out), identity)
+        return self.bn2(self.conv2(out), identity, split=SPLIT_RESGRAD and self.training)
 
 
 class Bottleneck(nn.Module):
@@ -95,10 +106,11 @@ class Bottleneck(nn.Module):
         self.stride = stride
 
     def forward(self, x):
-        identity = x if self.downsample is None else self.downsample(x)
+        x, skip = _pair(x)
+        identity = skip if self.downsample is None else self.downsample(skip)
         out = conv1x1_bn_act(x, self.conv1, self.bn1, enabled=FUSED_CONV1X1)
         out = self.bn2(self.conv2(out))
-        return conv1x1_bn_act(out, self.conv3, self.bn3, identity, enabled=FUSED_CONV1X1)
+        return conv1x1_bn_act(out, self.conv3, self.bn3, identity, enabled=FUSED_CONV1X1, split=SPLIT_RESGRAD and self.training)
 
 
 class ResNet(nn.Module):
@@ -151,6 +163,7 @@ class ResNet(nn.Module):
                             training=bn.training or not bn.track_running_stats, momentum=0.1 if bn.momentum is None else bn.momentum,
                             eps=bn.eps, fused=bn.fused, num_batches_tracked=nbt)
         x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
+        x = _pair(x)[0]               # the last block has a single consumer: its second alias stays unused (gradient None)
         return self.fc(torch.flatten(self.avgpool(x), 1))
 
 

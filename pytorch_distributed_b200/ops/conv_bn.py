@@ -39,18 +39,22 @@ def can_fuse_conv1x1(x, conv) -> bool:
             and x.size(0) * x.size(2) * x.size(3) >= 128)
 
 
-def conv1x1_bn_act(x, conv, bn, residual=None, enabled=True):
-    """relu?(bn(conv1x1(x)) + residual) for a ``nn.Conv2d`` and a :class:`BNAct` module."""
+def conv1x1_bn_act(x, conv, bn, residual=None, enabled=True, split=False):
+    """relu?(bn(conv1x1(x)) + residual) for a ``nn.Conv2d`` and a :class:`BNAct` module (``split``: see ``bn_act``)."""
     training = bn.training or not bn.track_running_stats
     if not (enabled and training and can_fuse_conv1x1(x, conv) and bn.fused is not False):
-        return bn(conv(x), residual)
+        return bn(conv(x), residual, split) if split else bn(conv(x), residual)
     nc = conv.weight.size(0)
     ws = workspace(x.device)
     work, gen = ws.take(4 * nc)
     y = _Conv1x1Stats.apply(x, conv.weight, work[: 2 * nc])
     if not _can_fuse(y, bn.weight, residual, bn.running_mean):
-        return bn(y, residual)       # (cannot happen for the shapes accepted above; keeps semantics if it ever does)
+        return bn(y, residual, split) if split else bn(y, residual)   # (cannot happen for the shapes accepted above)
     need_grad = torch.is_grad_enabled() and (y.requires_grad or bn.weight.requires_grad)
     nbt = bn.num_batches_tracked if (bn.training and bn.track_running_stats) else None
-    return _BnActFn.apply(y, residual, bn.weight, bn.bias, bn.running_mean, bn.running_var, nbt, True,
-                          0.1 if bn.momentum is None else float(bn.momentum), float(bn.eps), bn.relu, need_grad, (work, gen))
+    out = _BnActFn.apply(y, residual, bn.weight, bn.bias, bn.running_mean, bn.running_var, nbt, True,
+                         0.1 if bn.momentum is None else float(bn.momentum), float(bn.eps), bn.relu, need_grad, (work, gen),
+                         bool(split and need_grad))
+    if split and not isinstance(out, tuple):
+        return out, out
+    return out

@@ -27,6 +27,7 @@ WANT = {
     "bn_apply_bf16_relu_res": r"bn_apply_kernelI13__nv_bfloat16Lb1ELb1E",
     "bn_bwd_reduce_bf16_relu": r"bn_bwd_reduce_kernelI13__nv_bfloat16Lb1E",
     "bn_bwd_apply_bf16_relu_res": r"bn_bwd_apply_kernelI13__nv_bfloat16Lb1ELb1E",
+    "bn_bwd_reduce_sum_bf16_relu": r"bn_bwd_reduce_sum_kernelI13__nv_bfloat16Lb1E",
 }
 
 
