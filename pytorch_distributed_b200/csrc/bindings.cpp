@@ -95,7 +95,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("bn_act_backward", &bn_act_backward);
   m.def("bn_act_backward2", &bn_act_backward2);
   m.def("stem_forward", &stem_forward);
+  m.def("stem_forward_pre", &stem_forward_pre);
   m.def("stem_backward", &stem_backward);
+  m.def("stem_im2col", &stem_im2col);
   m.def("conv1x1_bnstats", &conv1x1_bnstats);
   m.def("normalize_nhwc", &normalize_nhwc);
   m.def("p2p_copy_multi", &p2p_copy_multi);

@@ -1007,13 +1007,14 @@ static PoolGeom pool_geom(const at::Tensor& x) {
 
 template <typename T>
 static void stem_fwd_impl(const at::Tensor& x, at::Tensor& y, at::Tensor& code, at::Tensor& work, at::Tensor& saved, const at::Tensor& w,
-                          const at::Tensor& b, at::Tensor& rm, at::Tensor& rv, at::Tensor& nbt, bool training, float momentum, float eps) {
+                          const at::Tensor& b, at::Tensor& rm, at::Tensor& rv, at::Tensor& nbt, bool training, float momentum, float eps,
+                          bool stats_ready) {
   const Geometry g = geometry(x);
   const PoolGeom pg = pool_geom(x);
   cudaStream_t st = at::cuda::getCurrentCUDAStream();
   const T* xp = reinterpret_cast<const T*>(x.data_ptr());
   float* wk = work.defined() ? work.data_ptr<float>() : nullptr;
-  if (training) {
+  if (training && !stats_ready) {      // stats_ready: the producing GEMM already reduced sum / sum-of-squares into `work`
     int rpb;
     const int grid = reduce_grid(g, &rpb, resident_ctas(bn_stats_kernel<T>, g.smem));
     bn_stats_kernel<T><<<grid, kBnThreads, g.smem, st>>>(xp, wk, g.M, g.C, rpb);
@@ -1033,9 +1034,10 @@ static void stem_fwd_impl(const at::Tensor& x, at::Tensor& y, at::Tensor& code, 
 }
 
 // relu(bn(x)) -> maxpool 3x3/2/1.  returns {y_pool, saved, code}
-std::vector<at::Tensor> stem_forward(const at::Tensor& x, const at::Tensor& weight, const at::Tensor& bias, at::Tensor running_mean,
-                                     at::Tensor running_var, c10::optional<at::Tensor> num_batches_tracked, bool training, double momentum,
-                                     double eps, bool need_code, at::Tensor work) {
+static std::vector<at::Tensor> stem_forward_common(const at::Tensor& x, const at::Tensor& weight, const at::Tensor& bias,
+                                                   at::Tensor running_mean, at::Tensor running_var,
+                                                   c10::optional<at::Tensor> num_batches_tracked, bool training, double momentum, double eps,
+                                                   bool need_code, at::Tensor work, bool stats_ready) {
   check_nhwc(x, "x");
   const int C = (int)x.size(1);
   TORCH_CHECK(C % 8 == 0 && kBnThreads % (C / 8) == 0, "fused stem needs C/8 to divide ", kBnThreads);
@@ -1052,12 +1054,24 @@ std::vector<at::Tensor> stem_forward(const at::Tensor& x, const at::Tensor& weig
   }
   if (need_code) code = at::empty({y.numel()}, x.options().dtype(at::kByte));
   switch (x.scalar_type()) {
-    case at::kBFloat16: stem_fwd_impl<__nv_bfloat16>(x, y, code, work, saved, weight, bias, running_mean, running_var, nbt, training, (float)momentum, (float)eps); break;
-    case at::kHalf: stem_fwd_impl<__half>(x, y, code, work, saved, weight, bias, running_mean, running_var, nbt, training, (float)momentum, (float)eps); break;
-    case at::kFloat: stem_fwd_impl<float>(x, y, code, work, saved, weight, bias, running_mean, running_var, nbt, training, (float)momentum, (float)eps); break;
+    case at::kBFloat16: stem_fwd_impl<__nv_bfloat16>(x, y, code, work, saved, weight, bias, running_mean, running_var, nbt, training, (float)momentum, (float)eps, stats_ready); break;
+    case at::kHalf: stem_fwd_impl<__half>(x, y, code, work, saved, weight, bias, running_mean, running_var, nbt, training, (float)momentum, (float)eps, stats_ready); break;
+    case at::kFloat: stem_fwd_impl<float>(x, y, code, work, saved, weight, bias, running_mean, running_var, nbt, training, (float)momentum, (float)eps, stats_ready); break;
     default: TORCH_CHECK(false, "unsupported activation dtype");
   }
   return {y, saved, code};
+}
+
+std::vector<at::Tensor> stem_forward(const at::Tensor& x, const at::Tensor& weight, const at::Tensor& bias, at::Tensor running_mean,
+                                     at::Tensor running_var, c10::optional<at::Tensor> num_batches_tracked, bool training, double momentum,
+                                     double eps, bool need_code, at::Tensor work) {
+  return stem_forward_common(x, weight, bias, running_mean, running_var, num_batches_tracked, training, momentum, eps, need_code, work, false);
+}
+// same, with the per-channel sum / sum of squares of x already accumulated in work[0:2C] (stem convolution run as a GEMM)
+std::vector<at::Tensor> stem_forward_pre(const at::Tensor& x, const at::Tensor& weight, const at::Tensor& bias, at::Tensor running_mean,
+                                         at::Tensor running_var, c10::optional<at::Tensor> num_batches_tracked, bool training, double momentum,
+                                         double eps, bool need_code, at::Tensor work) {
+  return stem_forward_common(x, weight, bias, running_mean, running_var, num_batches_tracked, training, momentum, eps, need_code, work, true);
 }
 
 template <typename T>

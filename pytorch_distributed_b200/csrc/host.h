@@ -54,11 +54,17 @@ std::vector<at::Tensor> bn_act_backward2(const at::Tensor& dy_a, const at::Tenso
 std::vector<at::Tensor> stem_forward(const at::Tensor& x, const at::Tensor& weight, const at::Tensor& bias, at::Tensor running_mean,
                                      at::Tensor running_var, c10::optional<at::Tensor> num_batches_tracked, bool training, double momentum,
                                      double eps, bool need_code, at::Tensor work);
+std::vector<at::Tensor> stem_forward_pre(const at::Tensor& x, const at::Tensor& weight, const at::Tensor& bias, at::Tensor running_mean,
+                                         at::Tensor running_var, c10::optional<at::Tensor> num_batches_tracked, bool training, double momentum,
+                                         double eps, bool need_code, at::Tensor work);
 std::vector<at::Tensor> stem_backward(const at::Tensor& dp, const at::Tensor& x, const at::Tensor& code, const at::Tensor& weight,
                                       const at::Tensor& saved, at::Tensor work);
 
 // ---- gemm_bnstats.cu (tcgen05 / TMA / TMEM)
 at::Tensor conv1x1_bnstats(const at::Tensor& x, const at::Tensor& weight, at::Tensor gsum);
+
+// ---- stem_conv.cu
+at::Tensor stem_im2col(const at::Tensor& x);
 
 // ---- data_ops.cu
 at::Tensor normalize_nhwc(const at::Tensor& src, const at::Tensor& mean, const at::Tensor& std, int64_t out_dtype, bool channels_last);

@@ -17,6 +17,7 @@ import torch.nn as nn
 from ..ops.bn_act import begin_step, bn_act
 from ..ops.conv_bn import conv1x1_bn_act
 from ..ops.stem import bn_relu_maxpool
+from ..ops.stem_conv import can_use_stem_gemm, stem_conv_bn_relu_maxpool
 
 # 1x1 conv -> BN pairs run as ONE tcgen05 GEMM with the BN statistics in its epilogue (ops/conv_bn.py,
 # profiles/gemm_bnstats_probe.md: -23 % vs cuDNN conv + separate statistics pass over the ResNet-50 shapes).
@@ -28,6 +29,9 @@ FUSED_CONV1X1 = _os.environ.get("PTD_FUSED_CONV1X1", "1") == "1"
 # summed inside the BN-backward reduction pass (csrc/bn_act.cu: bn_act_backward2) instead of by an autograd add:
 # 7 instead of 9 tensor passes over the widest activations.  Opt-in until it has been timed on hardware.
 SPLIT_RESGRAD = _os.environ.get("PTD_SPLIT_RESGRAD", "0") == "1"
+# Stem 7x7 convolution as im2col + the tcgen05 GEMM with fused BN statistics instead of cuDNN's legacy C_in = 3 kernels
+# (ops/stem_conv.py).  Opt-in until it has been timed on hardware.
+STEM_GEMM = _os.environ.get("PTD_STEM_GEMM", "0") == "1"
 
 
 def _pair(x):
@@ -158,6 +162,11 @@ class ResNet(nn.Module):
         if self.training:
             begin_step(x.device)      # recycle the BN accumulator workspace: one memset per step
         bn = self.bn1
+        if STEM_GEMM and bn.training and torch.is_grad_enabled() and bn.fused is not False and (
+                can_use_stem_gemm(x, self.conv1) or bn.fused == "emulate"):
+            x = stem_conv_bn_relu_maxpool(x, self.conv1, bn, emulate=bn.fused == "emulate")
+            x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
+            return self.fc(torch.flatten(self.avgpool(_pair(x)[0]), 1))
         nbt = bn.num_batches_tracked if (bn.training and bn.track_running_stats) else None
         x = bn_relu_maxpool(self.conv1(x), bn.weight, bn.bias, bn.running_mean, bn.running_var,   # fused stem tail
                             training=bn.training or not bn.track_running_stats, momentum=0.1 if bn.momentum is None else bn.momentum,

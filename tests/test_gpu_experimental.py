@@ -70,3 +70,71 @@ def test_resnet50_step_with_split_residual_gradients():
     # the fused sum is rounded exactly like the eager add, so the gradients should agree bit for bit
     worst = max(((outs[0][1][n] - outs[1][1][n]).abs().max() / (outs[0][1][n].abs().max() + 1e-12)).item() for n in outs[0][1])
     assert worst < 1e-2, worst
+
+
+@pytest.mark.parametrize("shape", [(4, 3, 64, 64), (2, 3, 75, 91), (16, 3, 224, 224)])
+def test_stem_im2col_kernel_matches_definition(shape):
+    from pytorch_distributed_b200 import _ext
+    from pytorch_distributed_b200.ops.stem_conv import im2col_reference
+    torch.manual_seed(0)
+    x = torch.randn(shape, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last)
+    a = _ext.lib().stem_im2col(x)
+    ref = im2col_reference(x)
+    assert a.shape == ref.shape and a.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(a, ref)
+
+
+def test_stem_gemm_path_matches_cudnn_path():
+    """conv7x7 + BN + ReLU + MaxPool: im2col + tcgen05 GEMM (+ statistics) + stem_forward_pre vs cuDNN conv + fused stem tail."""
+    import copy
+    import torch.nn as nn
+    from pytorch_distributed_b200.models.resnet import BNAct
+    from pytorch_distributed_b200.ops.bn_act import begin_step
+    from pytorch_distributed_b200.ops.stem import bn_relu_maxpool
+    from pytorch_distributed_b200.ops.stem_conv import can_use_stem_gemm, stem_conv_bn_relu_maxpool
+    torch.manual_seed(0)
+    dev = torch.device("cuda", 0)
+    conv = nn.Conv2d(3, 64, 7, stride=2, padding=3, bias=False).to(dev).bfloat16().to(memory_format=torch.channels_last)
+    bn = BNAct(64).to(dev).train()
+    x = torch.randn(32, 3, 224, 224, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
+    assert can_use_stem_gemm(x, conv)
+    res = []
+    for mode in ("cudnn", "gemm"):
+        c, b = copy.deepcopy(conv), copy.deepcopy(bn)
+        begin_step(dev)
+        if mode == "gemm":
+            y = stem_conv_bn_relu_maxpool(x, c, b)
+        else:
+            y = bn_relu_maxpool(c(x), b.weight, b.bias, b.running_mean, b.running_var, training=True, momentum=0.1, eps=b.eps,
+                                num_batches_tracked=b.num_batches_tracked)
+        (y.float() * torch.linspace(-1, 1, y.numel(), device=dev).view_as(y)).sum().backward()
+        res.append((y.float(), c.weight.grad.float(), b.weight.grad.float(), b.bias.grad.float(), b.running_mean.clone(), b.running_var.clone()))
+    torch.cuda.synchronize()
+    names = ("y", "dW", "dgamma", "dbeta", "running_mean", "running_var")
+    for n, a, e in zip(names, res[1], res[0]):
+        err = (a - e).abs().max().item() / (e.abs().max().item() + 1e-6)
+        assert err < 3e-2, (n, err)
+
+
+def test_resnet50_step_with_stem_gemm():
+    import copy
+    import pytorch_distributed_b200.models.resnet as R
+    from pytorch_distributed_b200.models import create_model
+    torch.manual_seed(0)
+    dev = torch.device("cuda", 0)
+    base = create_model("resnet50", num_classes=100).to(dev).to(memory_format=torch.channels_last).bfloat16()
+    x = torch.randn(16, 3, 128, 128, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
+    y = torch.randint(0, 100, (16,), device=dev)
+    outs = []
+    for flag in (False, True):
+        m = copy.deepcopy(base).train()
+        R.STEM_GEMM = flag
+        try:
+            out = m(x)
+            torch.nn.functional.cross_entropy(out.float(), y).backward()
+        finally:
+            R.STEM_GEMM = False
+        outs.append((out.float(), m.conv1.weight.grad.float()))
+    torch.cuda.synchronize()
+    assert (outs[0][0] - outs[1][0]).abs().max().item() < 0.1 * outs[0][0].abs().max().item()
+    assert (outs[0][1] - outs[1][1]).abs().max().item() < 0.1 * outs[0][1].abs().max().item()

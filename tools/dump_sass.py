@@ -41,7 +41,7 @@ def main():
         if not hit:
             summary.append("%-32s NOT FOUND (%s)" % (name, pat))
             continue
-        body = hit[0]
+        body = hit[0].split("\nFatbin elf code")[0].rstrip() + "\n"      # the next translation unit's header is not part of it
         with open(os.path.join(OUT, name + ".sass"), "w") as f:
             f.write("Function : " + body)
         ops = re.findall(r"^\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_.]+)", body, flags=re.M)
