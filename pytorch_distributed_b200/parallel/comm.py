@@ -82,7 +82,7 @@ class FusedCommunicator:
             arena_bytes = int(os.environ.get("PTD_ARENA_MB", "1024")) << 20
         timeout_ms = int(os.environ.get("PTD_COMM_TIMEOUT_MS", timeout_ms))
         self.max_blocks = self._C.MAX_BLOCKS
-        self.max_ctas = min(max_ctas, self.max_blocks)
+        self.max_ctas = min(int(os.environ.get("PTD_MAX_CTAS", max_ctas)), self.max_blocks)   # CTAs per collective (<= 64): sweepable
         self.header_bytes = P.round_up(self._C.SIGNAL_PAD_BYTES, 128 << 10)
         self._bump = self.header_bytes
         self._next_channel = 0
