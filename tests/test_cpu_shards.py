@@ -225,3 +225,30 @@ def test_entrypoint_trains_from_shards(tmp_path):
     assert r.stdout.count("Epoch: [0][0/3]") == 2          # 12 train images / 2 ranks / batch 2
     assert r.stdout.count(" * Acc@1") == 2
     assert (tmp_path / "checkpoint.pth.tar").exists()
+
+
+def test_abandoned_epoch_and_restart(tmp_path):
+    paths, _ = _write(tmp_path, n=64)
+    ld = shards.ShardLoader(paths, 4, 12, train=True, seed=3, workers=3, depth=3, pin=False, with_ids=True)
+    first = []
+    for i, (x, y) in enumerate(ld):
+        first.append(ld.last_ids.tolist())
+        if i == 2:
+            break                                   # consumer walks away mid-epoch (e.g. --steps-per-epoch)
+    again = [ld.last_ids.tolist() for _ in ld]      # same epoch number -> same order, from the start
+    assert again[:3] == first and len(again) == 16
+    ld.close()
+
+
+def test_corrupt_shard_is_rejected(tmp_path):
+    paths, _ = _write(tmp_path, n=5)
+    bad = tmp_path / "train-99999.ptds"
+    data = bytearray(open(paths[0], "rb").read())
+    data[:8] = b"NOTASHRD"
+    bad.write_bytes(bytes(data))
+    with pytest.raises(RuntimeError, match="not a PTDSHRD1 shard"):
+        shards.ShardLoader([str(bad)], 2, 8, pin=False)
+    trunc = tmp_path / "train-99998.ptds"
+    trunc.write_bytes(open(paths[0], "rb").read()[:200])
+    with pytest.raises(RuntimeError, match="corrupt shard record|truncated shard index"):
+        shards.ShardLoader([str(trunc)], 2, 8, pin=False)
