@@ -274,7 +274,9 @@ def run_own(a):
                        "parallelism": "dp%d" % (a.gpus if dp else world), "entry": a.entry, "comm": getattr(comm, "backend", "none"),
                        "nvls": bool(getattr(comm, "nvls", False)), "channels_last": bool(args.channels_last),
                        "fused_bn": args.fused_bn is not False, "optimizer": a.optimizer, "cuda_graph": step.graph is not None,
-                       "l2_policy": "inputs larger than L2 (4 x 38.5 MB bf16 batches + GBs of activations per step)"},
+                       "l2_policy": "inputs larger than L2 (4 x 38.5 MB bf16 batches + GBs of activations per step)",
+                       "opt_in": {k: os.environ[k] for k in ("PTD_SPLIT_RESGRAD", "PTD_STEM_GEMM", "PTD_FUSED_CONV1X1", "PTD_MAX_CTAS",
+                                                             "PTD_NVLS") if k in os.environ}},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "impl": "own", "host_enqueue_ms_per_step": host_ms,
             "final_loss": losses.val,
         }
