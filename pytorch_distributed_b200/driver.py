@@ -578,7 +578,7 @@ def validate(val_loader, model, criterion, st: Strategy, device, args):
                 if not args.quiet:
                     progress.display(i)
         metrics.drain()
-        # TODO(reference parity): this line is printed by every rank, like the reference
+        # printed by every rank, like the reference (/root/reference/distributed.py:320-321)
         print(" * Acc@1 {top1.avg:.3f} Acc@5 {top5.avg:.3f}".format(top1=top1, top5=top5), flush=True)
     _log_jsonl(args, {"phase": "val", "rank": st.rank() if st.distributed else 0, "loss": losses.avg, "acc1": top1.avg, "acc5": top5.avg})
     return top1.avg
