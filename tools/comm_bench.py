@@ -75,6 +75,41 @@ def main():
             bus = 2 * (world - 1) / world * n * wbytes / (best * 1e-3) / 1e9
             busn = 2 * (world - 1) / world * n * wbytes / (t_nccl * 1e-3) / 1e9
             say("| %d | %s | %.1f | %.1f | %.1f | %.0f | %.2f | %.0f |" % (n, wire, t_nvls * 1e3, t_p2p * 1e3, t_nccl * 1e3, bus, bus / 725.0, busn))
+    # ---- K1 with a wider grid (64 CTAs) for the big messages, where a 32-CTA pack phase cannot stream HBM fast enough
+    say("\n## K1 two-shot NVLS: 32 vs 64 CTAs\n")
+    say("| elements | wire | 32 CTAs us | 64 CTAs us |\n|---:|---|---:|---:|")
+    for n in (1 << 24, 25_600_000, 1 << 26):
+        for wire in ("bf16", "fp32"):
+            src = torch.randn(n, device=dev)
+            plans = {c: comm.make_plan([n], wire, max_ctas=c) for c in (32, 64)}
+            ts = {}
+            for c, pl in plans.items():
+                fn = lambda pl=pl: comm.run(pl, [src], KIND_TWO_SHOT, comm.misc_channel, scale=1.0 / world, writeback=False, nvls=comm.nvls)
+                for _ in range(3):
+                    fn()
+                ts[c] = timed(fn, 7, dev, sync)
+            say("| %d | %s | %.1f | %.1f |" % (n, wire, ts[32] * 1e3, ts[64] * 1e3))
+    # ---- K2: broadcast of a ResNet-50-shaped tensor list from rank 0 (DDP constructor / per-forward buffer sync)
+    from pytorch_distributed_b200.models import create_model
+    model = create_model("resnet50").to(dev)
+    params = [p.data for p in model.parameters()]
+    bufs = [b for b in model.buffers() if b.is_floating_point()]
+    say("\n## K2 broadcast from rank 0 (ResNet-50 tensor lists)\n")
+    say("| tensors | elements | fused us | NCCL (flatten + broadcast + unflatten) us |\n|---:|---:|---:|---:|")
+    for name, ts_ in (("parameters", params), ("BN buffers", bufs)):
+        def fused_b(ts_=ts_):
+            comm.broadcast_(ts_, root=0)
+
+        def nccl_b(ts_=ts_):
+            flat = torch._utils._flatten_dense_tensors(ts_)
+            dist.broadcast(flat, src=0)
+            for t, f in zip(ts_, torch._utils._unflatten_dense_tensors(flat, ts_)):
+                t.copy_(f)
+
+        for _ in range(3):
+            fused_b(); nccl_b()
+        tf, tn = timed(fused_b, 7, dev, sync), timed(nccl_b, 7, dev, sync)
+        say("| %d (%s) | %d | %.1f | %.1f |" % (len(ts_), name, sum(t.numel() for t in ts_), tf * 1e3, tn * 1e3))
     # ---- latency: per-iteration metric synchronisation
     logits = torch.randn(256, 1000, device=dev).bfloat16()
     target = torch.randint(0, 1000, (256,), device=dev)
