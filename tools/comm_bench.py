@@ -79,12 +79,13 @@ def main():
     say("\n## K1 two-shot NVLS: 32 vs 64 CTAs\n")
     say("| elements | wire | 32 CTAs us | 64 CTAs us |\n|---:|---|---:|---:|")
     for n in (1 << 24, 25_600_000, 1 << 26):
+        wide = FusedCommunicator(device=dev, arena_bytes=1 << 30)      # plans are never freed: a fresh 1 GiB arena per size
         for wire in ("bf16", "fp32"):
             src = torch.randn(n, device=dev)
-            plans = {c: comm.make_plan([n], wire, max_ctas=c) for c in (32, 64)}
+            plans = {c: wide.make_plan([n], wire, max_ctas=c) for c in (32, 64)}
             ts = {}
             for c, pl in plans.items():
-                fn = lambda pl=pl: comm.run(pl, [src], KIND_TWO_SHOT, comm.misc_channel, scale=1.0 / world, writeback=False, nvls=comm.nvls)
+                fn = lambda pl=pl: wide.run(pl, [src], KIND_TWO_SHOT, wide.misc_channel, scale=1.0 / world, writeback=False, nvls=wide.nvls)
                 for _ in range(3):
                     fn()
                 ts[c] = timed(fn, 7, dev, sync)
@@ -92,13 +93,14 @@ def main():
     # ---- K2: broadcast of a ResNet-50-shaped tensor list from rank 0 (DDP constructor / per-forward buffer sync)
     from pytorch_distributed_b200.models import create_model
     model = create_model("resnet50").to(dev)
+    bcomm = FusedCommunicator(device=dev, arena_bytes=1 << 30)
     params = [p.data for p in model.parameters()]
     bufs = [b for b in model.buffers() if b.is_floating_point()]
     say("\n## K2 broadcast from rank 0 (ResNet-50 tensor lists)\n")
     say("| tensors | elements | fused us | NCCL (flatten + broadcast + unflatten) us |\n|---:|---:|---:|---:|")
     for name, ts_ in (("parameters", params), ("BN buffers", bufs)):
         def fused_b(ts_=ts_):
-            comm.broadcast_(ts_, root=0)
+            bcomm.broadcast_(ts_, root=0)
 
         def nccl_b(ts_=ts_):
             flat = torch._utils._flatten_dense_tensors(ts_)
