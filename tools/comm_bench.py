@@ -92,7 +92,10 @@ def main():
             say("| %d | %s | %.1f | %.1f |" % (n, wire, ts[32] * 1e3, ts[64] * 1e3))
     # ---- K2: broadcast of a ResNet-50-shaped tensor list from rank 0 (DDP constructor / per-forward buffer sync)
     from pytorch_distributed_b200.models import create_model
-    model = create_model("resnet50").to(dev)
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = create_model("resnet50").to(dev)
     bcomm = FusedCommunicator(device=dev, arena_bytes=1 << 30)
     params = [p.data for p in model.parameters()]
     bufs = [b for b in model.buffers() if b.is_floating_point()]
