@@ -127,7 +127,7 @@ def stem_conv_bn_relu_maxpool(x, conv, bn, emulate: bool = False):
                                fused=False, num_batches_tracked=nbt)
     ws = workspace(x.device)
     work, gen = ws.take(4 * nc)
-    y = _StemConvFn.apply(x, conv.weight, work[: 2 * nc])
+    y = _StemConvFn.apply(x, conv.weight, work[: 2 * nc], False)      # always 4 inputs: backward returns 4 gradients
     if not can_fuse_stem(y, bn.weight, bn.running_mean):
         raise RuntimeError("stem GEMM output does not fit the fused stem tail")
     need_grad = torch.is_grad_enabled() and (y.requires_grad or bn.weight.requires_grad)
