@@ -91,7 +91,12 @@ class _StemConvFn(torch.autograd.Function):
         rows = a.permute(0, 2, 3, 1).reshape(-1, K_PAD)
         if dy2.dtype != rows.dtype:
             dy2 = dy2.to(rows.dtype)
-        dwp = dy2.t() @ rows                                           # [C_out, 192], reduction over all output pixels
+        # [C_out, 192], a reduction over millions of output pixels: fp32 result, so that the library's split-K partial sums are
+        # not rounded to 16 bits on the way (cuDNN's wgrad accumulates in fp32 too)
+        if rows.is_cuda and rows.dtype != torch.float32:
+            dwp = torch.mm(dy2.t(), rows, out_dtype=torch.float32)
+        else:
+            dwp = dy2.float().t() @ rows.float()
         return None, unpack_stem_weight(dwp, weight), None, None
 
 

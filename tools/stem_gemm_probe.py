@@ -45,7 +45,7 @@ def main():
     rows = a.permute(0, 2, 3, 1).reshape(-1, K_PAD)
     dy2 = dy.permute(0, 2, 3, 1).reshape(-1, 64)
     dw_ref = torch.ops.aten.convolution_backward(dy, x, w, None, (2, 2), (3, 3), (1, 1), False, (0, 0), 1, (False, True, False))[1]
-    dwp = dy2.t() @ rows
+    dwp = torch.mm(dy2.t(), rows, out_dtype=torch.float32)
     from pytorch_distributed_b200.ops.stem_conv import unpack_stem_weight
     werr = (unpack_stem_weight(dwp, w).float() - dw_ref.float()).abs().max().item() / dw_ref.float().abs().max().item()
     m = rows.size(0)
@@ -62,8 +62,10 @@ def main():
     print("| im2col kernel | %.0f | %.2f | %.0f |" % (t, gb_a + x.numel() * 2 / 1e9, (gb_a + x.numel() * 2 / 1e9) / t * 1e6))
     t = timed(lambda: C.conv1x1_bnstats(a, wp.view(64, K_PAD, 1, 1), stats))
     print("| tcgen05 GEMM K=192 N=64 + BN statistics | %.0f | %.2f | %.0f |" % (t, gb_a + gb_y, (gb_a + gb_y) / t * 1e6))
+    t = timed(lambda: torch.mm(dy2.t(), rows, out_dtype=torch.float32))
+    print("| library wgrad GEMM (dY^T x A), fp32 out | %.0f | %.2f | %.0f |" % (t, gb_a + gb_y, (gb_a + gb_y) / t * 1e6))
     t = timed(lambda: dy2.t() @ rows)
-    print("| library wgrad GEMM (dY^T x A) | %.0f | %.2f | %.0f |" % (t, gb_a + gb_y, (gb_a + gb_y) / t * 1e6))
+    print("| library wgrad GEMM (dY^T x A), bf16 out | %.0f | %.2f | %.0f |" % (t, gb_a + gb_y, (gb_a + gb_y) / t * 1e6))
     t = timed(lambda: pack_stem_weight(w))
     print("| weight packing (ATen) | %.0f | | |" % t)
 
