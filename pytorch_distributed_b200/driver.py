@@ -371,7 +371,8 @@ class HorovodStrategy(Strategy):
     """/root/reference/horovod_distributed.py: broadcast_parameters + DistributedOptimizer(compression=fp16)."""
     name = "horovod_distributed"
     cast_params = False         # gradients come back decompressed to fp32 into p.grad: keep fp32 weights + autocast
-    graph_capable = False       # the fusion dispatcher is a host thread: not capturable
+    # the fusion dispatcher is a host thread: not capturable - unless the static schedule replaces it after the first step
+    graph_capable = os.environ.get("PTD_HVD_STATIC", "0") == "1"
 
     def init_process_group(self, args, local_rank, nprocs):
         from .parallel import hvd

@@ -228,6 +228,16 @@ class _FusionEngine:
         self.enabled = True
         self.queue = None
         self.thread = None
+        # Static schedule (PTD_HVD_STATIC=1): group composition only depends on hook order and sizes, so after the first complete
+        # step the recorded groups are frozen and the hooks launch them directly - no queue, no dispatcher thread, and the
+        # step becomes capturable in a CUDA graph.  Until then (and by default) requests go through the C++ fusion queue.
+        self._static_wanted = os.environ.get("PTD_HVD_STATIC", "0") == "1"
+        self._trace = []            # groups (tuples of parameter indices) launched by the dispatcher during the current step
+        self._schedule = None       # frozen trace
+        self._group_of: Dict[int, int] = {}
+        self._left = []
+        self._next_static = 0
+        self._fired = 0
         if comm.world > 1 or self.fused:
             C = _ext.lib() if self.fused or _ext.available() else None
             if C is not None:
@@ -252,6 +262,11 @@ class _FusionEngine:
             if self._counts[i] < self.passes:
                 return
             self._counts[i] = 0
+            if self._schedule is not None:          # static schedule: the last member of a group launches it
+                self._fired += 1
+                self._left[self._group_of[i]] -= 1
+                self._launch_ready_static()
+                return
             if self.queue is None:
                 return
             ev = None
@@ -268,17 +283,25 @@ class _FusionEngine:
         with _lock:
             ids = [self._handles.pop(h) for h in handles]
             evs = [self._events.pop(h) for h in handles]
+        self._trace.append(tuple(ids))
+        self._reduce(ids, evs[-1])                  # events are stream-ordered: the last one covers the group
+
+    def _reduce(self, ids, ready_event):
+        """One fused all-reduce (cast -> reduce -> average -> write back) over the gradients of parameters ``ids``."""
         grads = []
         for i in ids:
-            g = self.params[i].grad
+            p = self.params[i]
+            if p.grad is None:                      # unused in this step: contributes zeros, like every other rank's copy
+                p.grad = torch.zeros_like(p, memory_format=torch.preserve_format)
+            g = p.grad
             if not is_dense(g):
                 g = g.contiguous()
-                self.params[i].grad = g
+                p.grad = g
             grads.append(g)
         if self.fused:
             wire = self.wire or ("fp32" if grads[0].dtype == torch.float32 else ("bf16" if grads[0].dtype == torch.bfloat16 else "fp16"))
-            if evs[-1] is not None:
-                self.stream.wait_event(evs[-1])     # events are stream-ordered: the last one covers the group
+            if ready_event is not None:
+                self.stream.wait_event(ready_event)
             for lo in range(0, len(ids), 256):      # one kernel launch carries at most 256 tensor pointers
                 sub_ids, sub = tuple(ids[lo:lo + 256]), grads[lo:lo + 256]
                 plan = self._plans.get(sub_ids)     # response cache: the same fusion group recurs every step
@@ -289,6 +312,23 @@ class _FusionEngine:
                     self.comm.run(plan, sub, KIND_TWO_SHOT, self.channel, scale=1.0 / self.comm.world, writeback=True)
         else:
             self.comm.all_reduce_(grads, average=True, wire=self.wire)
+
+    # ------------------------------------------------------------------ static schedule
+    def _freeze(self, groups):
+        self._schedule = [tuple(g) for g in groups]
+        self._group_of = {i: k for k, g in enumerate(self._schedule) for i in g}
+        self._left = [len(g) for g in self._schedule]
+        self._next_static = 0
+        self._fired = 0
+
+    def _launch_ready_static(self, force: bool = False):
+        while self._next_static < len(self._schedule) and (force or self._left[self._next_static] == 0):
+            ev = None
+            if self.fused:
+                ev = torch.cuda.Event()
+                ev.record()                         # gradients of the group are complete on the current (compute) stream
+            self._reduce(list(self._schedule[self._next_static]), ev)
+            self._next_static += 1
 
     def _dispatch_loop(self):
         if self.fused:
@@ -309,6 +349,15 @@ class _FusionEngine:
 
     def synchronize(self):
         """Flush the open fusion group, wait until every request has been launched, join the comm stream."""
+        if self._schedule is not None:
+            if self._fired:                         # groups whose members did not all fire (unused parameters) go out now, in order
+                self._launch_ready_static(force=True)
+            self._left = [len(g) for g in self._schedule]
+            self._next_static = 0
+            self._fired = 0
+            if self.fused:
+                torch.cuda.current_stream().wait_stream(self.stream)
+            return
         if self.queue is None:
             return
         self.queue.flush()
@@ -321,6 +370,9 @@ class _FusionEngine:
             raise e
         if self.fused:
             torch.cuda.current_stream().wait_stream(self.stream)
+        trace, self._trace = self._trace, []
+        if self._static_wanted and trace and sorted(i for g in trace for i in g) == list(range(len(self.params))):
+            self._freeze(trace)                     # a complete step (every parameter exactly once): freeze its grouping
 
     def close(self):
         self._stop = True

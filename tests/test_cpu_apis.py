@@ -1,5 +1,6 @@
 """CPU tier for the wrapper APIs: hvd shim over gloo, apex namespace, prefetcher, metric pipeline, train step, reduce_mean."""
 import os
+import re
 import subprocess
 import sys
 
@@ -42,7 +43,13 @@ for it in range(3):
     opt.zero_grad()
     torch.nn.functional.cross_entropy(m(x), y).backward()
     opt.step()
+eng = opt._ptd_engine_obj
+if os.environ.get("PTD_HVD_STATIC") == "1":           # frozen after the first complete step; the hooks launched steps 2 and 3 themselves
+    assert eng._schedule is not None and sorted(i for g in eng._schedule for i in g) == list(range(len(eng.params)))
+else:
+    assert eng._schedule is None
 flat = torch.cat([p.detach().reshape(-1) for p in m.parameters()])
+print("HVD-SUM {} {:.10f}".format(r, flat.double().sum().item()))
 lo, hi = flat.clone(), flat.clone()
 torch.distributed.all_reduce(lo, op=torch.distributed.ReduceOp.MIN); torch.distributed.all_reduce(hi, op=torch.distributed.ReduceOp.MAX)
 assert torch.allclose(lo, hi, atol=1e-6), (lo - hi).abs().max()      # averaged gradients => identical weights on all ranks
@@ -59,13 +66,18 @@ torch.distributed.destroy_process_group()
 
 
 def test_hvd_api_over_gloo(tmp_path):
+    """Dynamic (fusion queue + dispatcher thread) and static (frozen schedule, hooks launch the groups) modes give the same weights."""
     script = tmp_path / "hvd_check.py"
     script.write_text(HVD % ROOT)
-    env = dict(os.environ, OMP_NUM_THREADS="1")
-    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-                        "--master-port", "29731", str(script)], env=env, capture_output=True, text=True, timeout=600)
-    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-3000:]
-    assert p.stdout.count("HVD-OK") == 2
+    sums = {}
+    for static, port in (("0", "29731"), ("1", "29733")):
+        env = dict(os.environ, OMP_NUM_THREADS="1", PTD_HVD_STATIC=static)
+        p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                            "--master-port", port, str(script)], env=env, capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-3000:]
+        assert p.stdout.count("HVD-OK") == 2
+        sums[static] = sorted(re.findall(r"HVD-SUM \d (-?\d+\.\d+)", p.stdout))      # ranks may interleave their lines
+    assert sums["0"] == sums["1"] and len(sums["0"]) == 2
 
 
 def test_apex_namespace_surface():

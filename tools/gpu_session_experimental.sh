@@ -14,6 +14,9 @@ run base PTD_NOOP=1
 run split PTD_SPLIT_RESGRAD=1
 run stem PTD_STEM_GEMM=1
 run both PTD_SPLIT_RESGRAD=1 PTD_STEM_GEMM=1
+# horovod entry, eager vs static schedule + CUDA graph (single GPU exercises hooks, queue and capture; 2+ GPUs: tools/gpu_session_8gpu.sh)
+timeout 300 python bench.py --gpus 1 --steps 20 --warmup 5 --skip-e2e --entry horovod_distributed > gpurun_out/bench_exp_hvd_eager.json 2> gpurun_out/bench_exp_hvd_eager.err
+PTD_HVD_STATIC=1 timeout 300 python bench.py --gpus 1 --steps 20 --warmup 5 --skip-e2e --entry horovod_distributed > gpurun_out/bench_exp_hvd_static.json 2> gpurun_out/bench_exp_hvd_static.err
 tail -n 3 gpurun_out/exp_tests.log
 cat gpurun_out/stem_gemm_probe.md
-for t in base split stem both; do echo "$t: $(grep -o '"ms_per_step": [0-9.]*' gpurun_out/bench_exp_$t.json)"; done
+for t in base split stem both hvd_eager hvd_static; do echo "$t: $(grep -o '"ms_per_step": [0-9.]*' gpurun_out/bench_exp_$t.json)"; done
