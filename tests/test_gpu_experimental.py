@@ -144,3 +144,28 @@ def test_resnet50_step_with_stem_gemm():
     torch.cuda.synchronize()
     assert (outs[0][0] - outs[1][0]).abs().max().item() < 0.1 * outs[0][0].abs().max().item()
     assert (outs[0][1] - outs[1][1]).abs().max().item() < 0.1 * outs[0][1].abs().max().item()
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_horovod_entrypoint_static_schedule(tmp_path, graph):
+    """PTD_HVD_STATIC=1: the fusion groups are frozen after the first step and launched from the hooks (optionally inside a CUDA graph);
+    the loss trajectory must match the dynamic (queue + dispatcher thread) run of the same seed."""
+    import re
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    n = min(torch.cuda.device_count(), 2)
+    base = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1"]
+    args = ["-a", "resnet18", "-b", str(16 * n), "--synthetic", "--steps-per-epoch", "8", "--val-steps", "1", "--epochs", "1", "--image-size", "64",
+            "-p", "1", "--lr", "0.01", "--seed", "3", "--checkpoint-dir", str(tmp_path)]
+    losses = {}
+    for static, port in (("0", "29851"), ("1", "29852")):
+        env = dict(os.environ, PTD_HVD_STATIC=static)
+        for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+            env.pop(k, None)
+        cmd = base + ["--master-port", port, os.path.join(root, "horovod_distributed.py")] + args + (["--cuda-graph"] if graph and static == "1" else [])
+        p = subprocess.run(cmd, env=env, cwd=root, capture_output=True, text=True, timeout=900)
+        assert p.returncode == 0, p.stdout[-3000:] + "\n" + p.stderr[-5000:]
+        losses[static] = [float(x) for x in re.findall(r"Loss (\d\.\d+e[+-]\d+)", p.stdout)]
+    assert len(losses["1"]) == len(losses["0"]) > 0
+    assert all(abs(a - b) <= 0.05 * max(1.0, abs(a)) for a, b in zip(losses["0"], losses["1"])), (losses["0"][:8], losses["1"][:8])
