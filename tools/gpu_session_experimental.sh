@@ -1,6 +1,6 @@
 #!/bin/bash
 # First GPU call of the next session: validate the opt-in paths written without hardware access and measure what they buy.
-#   /usr/local/graft/bin/gpurun --timeout 1500 -- bash tools/gpu_session_experimental.sh
+#   /usr/local/graft/bin/gpurun --timeout 1800 -- bash tools/gpu_session_experimental.sh
 # Everything lands in gpurun_out/ (scratch); copy the summaries worth keeping into profiles/.
 mkdir -p gpurun_out
 export PYTHONPATH=$PWD
