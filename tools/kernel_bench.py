@@ -90,6 +90,22 @@ def main():
         tag = "C=%d M=%d%s%s" % (ch, B * hw * hw, " relu" if relu else "", " +res" if res else "")
         row("bn_stats + bn_apply", tag, t_f, n * (2 + 2 + 2 + (2 if res else 0) + (0.125 if relu else 0)))
         row("bn_bwd_reduce + bn_bwd_apply", tag, t_b, n * (2 * (4 + (0.125 if relu else 0)) + 2 + (2 if (res and relu) else 0)))
+        if res and hasattr(C, "bn_act_backward2"):     # split residual gradients (PTD_SPLIT_RESGRAD): the add moves into the reduce pass
+            go2 = torch.randn_like(x)
+
+            def bwd_add():
+                xs, mask, ws, saved = state["y"].grad_fn.saved_tensors
+                work.zero_()
+                C.bn_act_backward(go + go2, xs, mask, ws, saved, relu, res, work)
+
+            def bwd_split():
+                xs, mask, ws, saved = state["y"].grad_fn.saved_tensors
+                work.zero_()
+                C.bn_act_backward2(go, go2, xs, mask, ws, saved, relu, work)
+
+            mk = 0.125 if relu else 0
+            row("ATen add + bn_bwd_reduce + bn_bwd_apply", tag, timeit(bwd_add), n * (6 + (4 + mk) + (4 + mk) + 4))
+            row("bn_bwd_reduce_sum + bn_bwd_apply (split gradients)", tag, timeit(bwd_split), n * ((6 + mk) + 2 + 4 + 2))
         for p in (x, r, w, b):
             if p is not None:
                 p.grad = None
