@@ -18,7 +18,6 @@ disk is untouched (its sha256 is checked against /root/reference when that is mo
 """
 from __future__ import annotations
 
-import hashlib
 import importlib.util
 import json
 import os
@@ -37,22 +36,17 @@ def _unavailable(why: str):
 
 
 def _load_ref():
+    from baseline import install_reference as inst
     path = os.path.join(REF_DIR, "distributed.py")
-    if not os.path.exists(path):
-        src = "/root/reference/distributed.py"
-        if os.path.exists(src):
-            os.makedirs(REF_DIR, exist_ok=True)
-            import shutil
-            for fn in os.listdir("/root/reference"):
-                if fn.endswith((".py", ".sh", ".txt")):
-                    shutil.copyfile(os.path.join("/root/reference", fn), os.path.join(REF_DIR, fn))
-        else:
-            _unavailable("baseline/_ref/distributed.py missing and /root/reference not mounted")
-    if os.path.exists("/root/reference/distributed.py"):
-        a = hashlib.sha256(open(path, "rb").read()).hexdigest()
-        b = hashlib.sha256(open("/root/reference/distributed.py", "rb").read()).hexdigest()
-        if a != b:
-            _unavailable("baseline/_ref/distributed.py differs from /root/reference/distributed.py")
+    try:
+        status = inst.install()            # no-op when baseline/_ref is present and matches the sha256 manifest
+    except Exception as e:  # noqa: BLE001
+        status = "install failed: %r" % (e,)
+    bad = inst.verify()
+    if bad:
+        sys.stderr.write("[bench --impl reference] REFERENCE ARM UNAVAILABLE: %s; files not matching the manifest: %s\n"
+                         "  run `python -c 'import __graft_entry__ as g; g.build()'` where /root/reference is mounted\n" % (status, bad))
+        _unavailable("baseline/_ref incomplete (%s): %s" % (status, ",".join(bad)))
     argv, sys.argv = sys.argv, ["distributed.py"]
     try:
         spec = importlib.util.spec_from_file_location("ref_distributed", path)

@@ -234,6 +234,19 @@ def run_own(a):
     metrics.drain()
     ms = max_over_ranks(ev0.elapsed_time(ev1), device)
     value = B * world * K / (ms / 1e3)
+    # PTD_TIMELINE=<prefix>: 3 extra steps under torch.profiler (CUPTI kernel records, also inside graph replays), written as
+    # <prefix>.rank<r>.json for tools/timeline_summary.py.  Outside the timed region: the profiler never touches a bench value.
+    if os.environ.get("PTD_TIMELINE"):
+        from torch.profiler import ProfilerActivity, profile
+        barrier_sync(device)
+        with profile(activities=[ProfilerActivity.CUDA]) as prof_tl:
+            for i in range(3):
+                step(*resident[i % len(resident)])
+            torch.cuda.synchronize(device)
+        metrics.drain()
+        if rank in (0, world - 1):
+            prof_tl.export_chrome_trace("%s.rank%d.json" % (os.environ["PTD_TIMELINE"], rank))
+        barrier_sync(device)
 
     # ---------------- phase B: end to end (pinned host -> device every step, metrics back to the host every step)
     e2e = None
