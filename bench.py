@@ -181,6 +181,7 @@ def run_own(a):
         argv += ["--gpus", ",".join(str(i) for i in range(a.gpus))]
     if a.no_fused_bn:
         argv.append("--no-fused-bn")
+    argv += os.environ.get("PTD_BENCH_ARGS", "").split()          # extra driver flags for ablations (recorded in config.opt_in)
     if a.entry == "apex_distributed":
         argv += ["--opt-level", a.opt_level]
         if a.precision == "bf16":
@@ -288,8 +289,11 @@ def run_own(a):
                        "nvls": bool(getattr(comm, "nvls", False)), "channels_last": bool(args.channels_last),
                        "fused_bn": args.fused_bn is not False, "optimizer": a.optimizer, "cuda_graph": step.graph is not None,
                        "l2_policy": "inputs larger than L2 (4 x 38.5 MB bf16 batches + GBs of activations per step)",
+                       "bucket_cap_mb": args.bucket_cap_mb, "overlap_optimizer": bool(getattr(optimizer, "_overlap", False)),
+                       "bucket_view": bool(getattr(args, "bucket_view", False)),
                        "opt_in": {k: os.environ[k] for k in ("PTD_SPLIT_RESGRAD", "PTD_STEM_GEMM", "PTD_FUSED_CONV1X1", "PTD_MAX_CTAS",
-                                                             "PTD_NVLS") if k in os.environ}},
+                                                             "PTD_NVLS", "PTD_BENCH_ARGS", "PTD_DEFERRED_BCAST", "PTD_METRICS_SIDE",
+                                                             "PTD_ONESHOT_MAX_BYTES", "PTD_HVD_STATIC") if k in os.environ}},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "impl": "own", "host_enqueue_ms_per_step": host_ms,
             "final_loss": losses.val,
         }

@@ -19,11 +19,34 @@ _WIRE = {torch.float16: "fp16", torch.bfloat16: "bf16", torch.float32: "fp32"}
 
 
 class DistributedDataParallel(nn.Module):
+    """apex.parallel.DistributedDataParallel arguments and what they do here:
+
+    ``message_size``              bucket size in ELEMENTS (apex default 1e7), fixed reverse-order buckets
+    ``delay_allreduce``           True: nothing is launched from the hooks, every bucket goes out at the end of backward
+    ``gradient_average``          divide by the world size (default) or leave the sum
+    ``gradient_predivide_factor`` apex divides by f before and multiplies by f/world after the all-reduce to keep an fp16 sum in
+                                  range; the fused kernel pre-scales in the pack pass and accumulates in fp32 (in the switch),
+                                  so only the net factor matters: 1/world with averaging, 1/f without
+    ``allreduce_always_fp32``     fp32 wire format
+    ``retain_allreduce_buffers``  ``self.allreduce_buffers`` = the per-bucket flat slices of the symmetric gradient arena
+    ``num_allreduce_streams`` > 1, ``allreduce_communicators``, ``allreduce_trigger_params``, ``shared_param`` are rejected:
+    there is one communication stream and one (symmetric-memory) communicator by design.
+    """
+
     def __init__(self, module: nn.Module, message_size: int = 10000000, delay_allreduce: bool = False, shared_param=None,
                  allreduce_trigger_params=None, retain_allreduce_buffers: bool = False, allreduce_always_fp32: bool = False,
                  num_allreduce_streams: int = 1, allreduce_communicators=None, gradient_average: bool = True,
                  gradient_predivide_factor: float = 1.0, comm="auto", wire_dtype=None, process_group=None):
         super().__init__()
+        if shared_param is not None:
+            raise ValueError("shared_param is no longer supported as an option (apex removed it as well); use delay_allreduce=True")
+        if allreduce_trigger_params is not None:
+            raise NotImplementedError("allreduce_trigger_params: buckets are fixed by message_size here, custom triggers are not supported")
+        if num_allreduce_streams != 1:
+            raise NotImplementedError("num_allreduce_streams=%r: the fused data plane uses exactly one communication stream" %
+                                      (num_allreduce_streams,))
+        if allreduce_communicators is not None:
+            raise NotImplementedError("allreduce_communicators: the symmetric-memory communicator is created internally")
         self.module = module
         params = [p for p in module.parameters() if p.requires_grad]
         device = params[0].device
@@ -43,11 +66,25 @@ class DistributedDataParallel(nn.Module):
             scaler.rebind_found_inf(comm.found_inf)
         sync_module_states(module, comm, root=0)
         esz = 2 if wire_dtype != "fp32" else 4
+        world = comm.world
+        scale = (1.0 / world) if gradient_average else (1.0 / float(gradient_predivide_factor))
         self.engine = GradientEngine(params, comm, wire_dtype=wire_dtype, bucket_cap_mb=message_size * esz / float(1 << 20),
                                      first_bucket_mb=message_size * esz / float(1 << 20), check_inf=check_inf,
-                                     average=gradient_average)
+                                     average=gradient_average, delay_allreduce=delay_allreduce, scale=scale, tail_bucket_mb=None)
         self.delay_allreduce = delay_allreduce
+        self.gradient_average = gradient_average
+        self.gradient_predivide_factor = gradient_predivide_factor
+        self.retain_allreduce_buffers = retain_allreduce_buffers
         self._buffers_f = _float_buffers(module)
+
+    @property
+    def allreduce_buffers(self):
+        """Flat per-bucket views of the reduced gradients (apex ``retain_allreduce_buffers``); fused data plane only."""
+        eng = self.engine
+        if not self.retain_allreduce_buffers or not eng.fused:
+            return []
+        flat = eng.grad_arena()
+        return [flat[b.elem_off:b.elem_off + b.region_elems] for b in eng.buckets]
 
     def forward(self, *inputs, **kwargs):
         return self.module(*inputs, **kwargs)

@@ -75,7 +75,9 @@ def build_parser(entry: str = "distributed") -> argparse.ArgumentParser:
                    help="gradient data plane: fused = sm_100a peer-memory kernels, nccl/gloo = library all-reduce")
     x.add_argument("--wire-dtype", default="bf16", choices=["bf16", "fp16", "fp32"],
                    help="gradient wire format of the fused all-reduce")
-    x.add_argument("--bucket-cap-mb", default=25.0, type=float)
+    x.add_argument("--bucket-cap-mb", default=8.0, type=float,
+                   help="gradient bucket size cap in MiB of wire data (torch's default is 25; NVSwitch has no per-link cost, "
+                        "so smaller buckets only buy earlier overlap; first bucket 1 MiB, tail bucket 1 MiB)")
     x.add_argument("--precision", default=None, choices=["fp32", "bf16", "fp16"],
                    help="compute precision (default: bf16 on CUDA, fp32 on CPU)")
     x.add_argument("--channels-last", dest="channels_last", action="store_true", default=None)
@@ -86,6 +88,11 @@ def build_parser(entry: str = "distributed") -> argparse.ArgumentParser:
     x.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
                    help="fused = hand-written multi-tensor SGD kernel; torch = torch.optim.SGD")
     x.add_argument("--cuda-graph", action="store_true", help="capture the train step in a CUDA graph")
+    x.add_argument("--overlap-optimizer", dest="overlap_optimizer", action="store_true", default=True,
+                   help="fused optimizer: update each gradient bucket right behind its all-reduce, inside backward (default)")
+    x.add_argument("--no-overlap-optimizer", dest="overlap_optimizer", action="store_false")
+    x.add_argument("--bucket-view", action="store_true",
+                   help="DDP gradient_as_bucket_view: p.grad are views of the symmetric arena (no write-back / pack pass)")
     x.add_argument("--device", default=None, help="cuda|cpu (default: cuda if available)")
     x.add_argument("--dist-backend", default=None, help="control-plane backend (default nccl on CUDA, gloo on CPU)")
     x.add_argument("--dist-url", default=None, help="override rendezvous URL")

@@ -72,10 +72,14 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def("launch_plan",
            [](std::shared_ptr<SymmArena> a, int channel, int as_rank, int kind, int wire_dtype, bool nvls, int grid, std::vector<at::Tensor> tensors,
               int64_t seg_begin_ptr, int64_t segs_ptr, int64_t data_off_bytes, int64_t block_elems, int64_t plan_calls_ptr, int64_t found_inf_ptr,
-              double scale, bool writeback, int root) {
+              double scale, bool writeback, int root, int flags, int64_t result_off_bytes) {
              launch_plan(a->ctx(channel, as_rank), kind, wire_dtype, nvls, grid, tensors, seg_begin_ptr, segs_ptr, data_off_bytes, block_elems,
-                         plan_calls_ptr, found_inf_ptr, scale, writeback, root);
-           })
+                         plan_calls_ptr, found_inf_ptr, scale, writeback, root, flags, result_off_bytes);
+           },
+           py::arg("channel"), py::arg("as_rank"), py::arg("kind"), py::arg("wire_dtype"), py::arg("nvls"), py::arg("grid"), py::arg("tensors"),
+           py::arg("seg_begin_ptr"), py::arg("segs_ptr"), py::arg("data_off_bytes"), py::arg("block_elems"), py::arg("plan_calls_ptr"),
+           py::arg("found_inf_ptr"), py::arg("scale"), py::arg("writeback"), py::arg("root"), py::arg("flags") = 0,
+           py::arg("result_off_bytes") = (int64_t)-1)
       .def("launch_barrier", [](std::shared_ptr<SymmArena> a, int channel) { launch_barrier(a->ctx(channel)); })
       .def("launch_metrics",
            [](std::shared_ptr<SymmArena> a, int channel, const at::Tensor& logits, const at::Tensor& target, c10::optional<at::Tensor> loss, at::Tensor out) {
@@ -104,7 +108,13 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
 
   // horovod-style fusion queue (background thread + tensor fusion scheduling), see hvd_core.cpp
   py::class_<FusionQueue, std::shared_ptr<FusionQueue>>(m, "FusionQueue")
-      .def(py::init<int64_t, double>(), py::arg("fusion_threshold_bytes"), py::arg("cycle_time_ms"))
+      .def(py::init<int64_t, double, int64_t>(), py::arg("fusion_threshold_bytes"), py::arg("cycle_time_ms"), py::arg("cycle_bytes") = 0)
+      .def("wait_idle", &FusionQueue::wait_idle, py::arg("timeout_ms"), py::call_guard<py::gil_scoped_release>())
+      .def("wake", &FusionQueue::wake)
+      .def("set_cycle_bytes", &FusionQueue::set_cycle_bytes)
+      .def("cycle_bytes", &FusionQueue::cycle_bytes)
+      .def("enable_timeline", &FusionQueue::enable_timeline)
+      .def("timeline", &FusionQueue::timeline)
       .def("enqueue", &FusionQueue::enqueue, py::arg("name"), py::arg("nbytes"), py::arg("order_key"))
       .def("next_group", &FusionQueue::next_group, py::arg("timeout_ms"), py::call_guard<py::gil_scoped_release>())
       .def("flush", &FusionQueue::flush)

@@ -43,7 +43,12 @@ struct PlanArgs {
   float scale;
   int writeback;             // 1 => unpack the reduced values into the tensors
   int root;                  // broadcast root
+  int flags;                 // kPrepacked: the gradients already live in the arena (bucket views): no pack pass, the scale
+                             //             is applied to the REDUCED values instead
+  int64_t result_off_bytes;  // one-shot: arena offset (bytes) of the range that receives the reduced values (-1: third
+                             //           region of the plan's own allocation)
 };
+constexpr int kPrepacked = 1;
 
 constexpr int kThreads = 512;
 
@@ -168,6 +173,17 @@ __device__ __forceinline__ V4 to_unit(const float (&acc)[sizeof(W) == 4 ? 4 : 8]
   }
 }
 template <typename W>
+__device__ __forceinline__ V4 scale_unit(const V4& v, float s) {
+  if constexpr (sizeof(W) == 4) {
+    return V4{__float_as_uint(__uint_as_float(v.x) * s), __float_as_uint(__uint_as_float(v.y) * s),
+              __float_as_uint(__uint_as_float(v.z) * s), __float_as_uint(__uint_as_float(v.w) * s)};
+  } else {
+    float2 a = Wire<W>::unpack2(v.x), b = Wire<W>::unpack2(v.y), c = Wire<W>::unpack2(v.z), d = Wire<W>::unpack2(v.w);
+    return V4{Wire<W>::pack2(a.x * s, a.y * s), Wire<W>::pack2(b.x * s, b.y * s), Wire<W>::pack2(c.x * s, c.y * s),
+              Wire<W>::pack2(d.x * s, d.y * s)};
+  }
+}
+template <typename W>
 __device__ __forceinline__ bool unit_nonfinite(const V4& v) {
   if constexpr (sizeof(W) == 4) {
     return !isfinite(__uint_as_float(v.x)) || !isfinite(__uint_as_float(v.y)) || !isfinite(__uint_as_float(v.z)) || !isfinite(__uint_as_float(v.w));
@@ -190,7 +206,9 @@ __global__ void __launch_bounds__(kThreads) fused_allreduce_kernel(const __grid_
                                                                    const __grid_constant__ PlanArgs a) {
   uint32_t seq = load_seq(c);
   W* local = reinterpret_cast<W*>(c.base[c.rank] + a.data_off_bytes);
-  pack_block<W>(pk, a, local);
+  const bool prepacked = (a.flags & kPrepacked) != 0;      // gradients are bucket views: autograd wrote them into the arena
+  const bool rescale = prepacked && a.scale != 1.0f;
+  if (!prepacked) pack_block<W>(pk, a, local);
   block_barrier(c, seq);
 
   constexpr int kUnitElems = 16 / sizeof(W);
@@ -208,12 +226,14 @@ __global__ void __launch_bounds__(kThreads) fused_allreduce_kernel(const __grid_
       for (int k = 0; k < U; ++k) v[k] = Multimem<W>::ld_reduce(mc + (int64_t)(u + k * kThreads) * 16);
 #pragma unroll
       for (int k = 0; k < U; ++k) {
+        if (rescale) v[k] = scale_unit<W>(v[k], a.scale);
         if (a.found_inf) bad |= unit_nonfinite<W>(v[k]);
         multimem_st(mc + (int64_t)(u + k * kThreads) * 16, v[k]);
       }
     }
     for (; u < units; u += kThreads) {
       V4 v = Multimem<W>::ld_reduce(mc + (int64_t)u * 16);
+      if (rescale) v = scale_unit<W>(v, a.scale);
       if (a.found_inf) bad |= unit_nonfinite<W>(v);
       multimem_st(mc + (int64_t)u * 16, v);
     }
@@ -222,6 +242,10 @@ __global__ void __launch_bounds__(kThreads) fused_allreduce_kernel(const __grid_
       float acc[sizeof(W) == 4 ? 4 : 8];
       const int64_t off = slice_off + (int64_t)u * 16;
       p2p_reduce_unit<W>(c, off, acc);
+      if (rescale) {
+#pragma unroll
+        for (int k = 0; k < (sizeof(W) == 4 ? 4 : 8); ++k) acc[k] *= a.scale;
+      }
       V4 v = to_unit<W>(acc);
       if (a.found_inf) bad |= unit_nonfinite<W>(v);
       for (int i = 0; i < c.world; ++i) st_sys(c.base[(c.rank + i) % c.world] + off, v);
@@ -238,58 +262,47 @@ __global__ void __launch_bounds__(kThreads) fused_allreduce_kernel(const __grid_
 }
 
 // ================================================================= K1b: one-shot all-reduce (small payloads)
-// Every rank reduces the WHOLE CTA range itself and writes straight into the destination tensors:
-// one network traversal instead of two; W x the link traffic, so only for latency-bound sizes.
+// Every rank reduces the WHOLE CTA range itself: one network traversal and ONE barrier instead of two; W x the link
+// traffic, so only for latency-bound sizes (the crossover is measured by tools/comm_bench.py).
+//   pack   : gradients -> staging[call & 1]   (double buffered: a peer may still be reading the previous call's pack)
+//   barrier: peers' packs visible
+//   reduce : in-switch sum (multimem.ld_reduce) or peer loads of the whole CTA range -> the RESULT range of the local arena
+//            (the bucket's slot of the gradient arena when an engine owns one: the flat optimizer reads it in place)
+//   unpack : (optional) result range -> gradient tensors
 template <typename W, bool NVLS>
 __global__ void __launch_bounds__(kThreads) oneshot_allreduce_kernel(const __grid_constant__ CommCtx c,
                                                                      const __grid_constant__ PtrPack pk,
                                                                      const __grid_constant__ PlanArgs a) {
   uint32_t seq = load_seq(c);
-  // double buffer: peers may still be reading the previous call's pack from my arena
   const uint32_t call = a.plan_calls[blockIdx.x];
   const int64_t half_bytes = (int64_t)gridDim.x * a.block_elems * sizeof(W);
-  const int64_t data_off = a.data_off_bytes + (call & 1) * half_bytes;
-  W* local = reinterpret_cast<W*>(c.base[c.rank] + data_off);
-  pack_block<W>(pk, a, local);
+  const int64_t stage_off = a.data_off_bytes + (call & 1) * half_bytes;
+  const int64_t result_off = a.result_off_bytes >= 0 ? a.result_off_bytes : a.data_off_bytes + 2 * half_bytes;
+  pack_block<W>(pk, a, reinterpret_cast<W*>(c.base[c.rank] + stage_off));
   block_barrier(c, seq);
   constexpr int kUnitElems = 16 / sizeof(W);
-  for (int s = a.seg_begin[blockIdx.x]; s < a.seg_begin[blockIdx.x + 1]; ++s) {
-    const Seg sg = a.segs[s];
-    const int nunits = (sg.len + kUnitElems - 1) / kUnitElems;  // arena is padded to 8 elements: reading the pad is safe
-    for (int u = threadIdx.x; u < nunits; u += kThreads) {
-      const int64_t off = data_off + (sg.arena_off + (int64_t)u * kUnitElems) * sizeof(W);
-      float f[sizeof(W) == 4 ? 4 : 8];
-      if constexpr (NVLS) {
-        V4 v = Multimem<W>::ld_reduce(c.mc_base + off);
-        if constexpr (sizeof(W) == 4) {
-          f[0] = __uint_as_float(v.x); f[1] = __uint_as_float(v.y); f[2] = __uint_as_float(v.z); f[3] = __uint_as_float(v.w);
-        } else {
-          float2 t;
-          t = Wire<W>::unpack2(v.x); f[0] = t.x; f[1] = t.y;
-          t = Wire<W>::unpack2(v.y); f[2] = t.x; f[3] = t.y;
-          t = Wire<W>::unpack2(v.z); f[4] = t.x; f[5] = t.y;
-          t = Wire<W>::unpack2(v.w); f[6] = t.x; f[7] = t.y;
-        }
-      } else {
-        p2p_reduce_unit<W>(c, off, f);
-      }
-      const int base_i = u * kUnitElems;
-#pragma unroll
-      for (int k = 0; k < kUnitElems; ++k) {
-        const int i = base_i + k;
-        if (i < sg.len) {
-          void* dst = pk.ptr[sg.tensor];
-          const int64_t di = sg.src_off + i;
-          switch (pk.dtype[sg.tensor]) {
-            case kF32:  reinterpret_cast<float*>(dst)[di] = f[k]; break;
-            case kBF16: reinterpret_cast<__nv_bfloat16*>(dst)[di] = __float2bfloat16_rn(f[k]); break;
-            default:    reinterpret_cast<__half*>(dst)[di] = __float2half_rn(f[k]); break;
-          }
-        }
-      }
+  const int64_t blk_bytes = (int64_t)blockIdx.x * a.block_elems * sizeof(W);
+  const int units = (int)(a.block_elems / kUnitElems);
+  bool bad = false;
+  for (int u = threadIdx.x; u < units; u += kThreads) {
+    const int64_t off = stage_off + blk_bytes + (int64_t)u * 16;
+    V4 v;
+    if constexpr (NVLS) {
+      v = Multimem<W>::ld_reduce(c.mc_base + off);
+    } else {
+      float acc[sizeof(W) == 4 ? 4 : 8];
+      p2p_reduce_unit<W>(c, off, acc);
+      v = to_unit<W>(acc);
     }
+    if (a.found_inf) bad |= unit_nonfinite<W>(v);
+    st_v4(c.base[c.rank] + result_off + blk_bytes + (int64_t)u * 16, v);
+  }
+  if (a.found_inf && __syncthreads_or(bad) && threadIdx.x == 0) {
+    // every rank reduced the same values, so every rank takes the same decision: a local store is enough
+    *reinterpret_cast<volatile uint32_t*>(a.found_inf) = 1u;
   }
   __syncthreads();
+  if (a.writeback) unpack_block<W>(pk, a, reinterpret_cast<const W*>(c.base[c.rank] + result_off), false);
   if (threadIdx.x == 0) a.plan_calls[blockIdx.x] = call + 1;
   store_seq(c, seq);
 }
@@ -543,7 +556,7 @@ static void launch_kind(int kind, int grid, cudaStream_t st, const CommCtx& c, c
 // kind: 0 two-shot all-reduce, 1 one-shot all-reduce, 2 broadcast, 3 pack, 4 reduce-to-caller, 5 push, 6 unpack
 void launch_plan(const CommCtx& ctx, int kind, int wire_dtype, bool nvls, int grid, const std::vector<at::Tensor>& tensors,
                  int64_t seg_begin_ptr, int64_t segs_ptr, int64_t data_off_bytes, int64_t block_elems, int64_t plan_calls_ptr,
-                 int64_t found_inf_ptr, double scale, bool writeback, int root) {
+                 int64_t found_inf_ptr, double scale, bool writeback, int root, int flags, int64_t result_off_bytes) {
   TORCH_CHECK(grid >= 1 && grid <= kMaxBlocks, "grid out of range");
   TORCH_CHECK(!nvls || ctx.mc_base != nullptr, "NVLS variant requested but no multicast mapping");
   PtrPack pk;
@@ -558,6 +571,8 @@ void launch_plan(const CommCtx& ctx, int kind, int wire_dtype, bool nvls, int gr
   a.scale = (float)scale;
   a.writeback = writeback ? 1 : 0;
   a.root = root;
+  a.flags = flags;
+  a.result_off_bytes = result_off_bytes;
   cudaStream_t st = at::cuda::getCurrentCUDAStream();
   switch (wire_dtype) {
     case kBF16: nvls ? launch_kind<__nv_bfloat16, true>(kind, grid, st, ctx, pk, a) : launch_kind<__nv_bfloat16, false>(kind, grid, st, ctx, pk, a); break;

@@ -78,6 +78,12 @@ class MetricPipeline:
             self.ring = [torch.zeros(4, dtype=torch.float32).pin_memory() for _ in range(depth)]
             self.dev = [torch.zeros(4, dtype=torch.float32, device=device) for _ in range(depth)]
             self.slot = 0
+        # the metric kernel waits for every peer's values (LL all-reduce): on the communicator's side stream that wait never
+        # stalls the compute stream (PTD_METRICS_SIDE=0 puts it back in line)
+        self.side = None
+        if self.cuda and self.reduce and getattr(comm, "backend", "") == "fused" and os.environ.get("PTD_METRICS_SIDE", "1") == "1":
+            self.side = comm.side_stream
+        self._side_dirty = False
 
     def push(self, output, target, loss, n: int) -> None:
         if not self.cuda:
@@ -91,14 +97,24 @@ class MetricPipeline:
             return
         dev = self.dev[self.slot]
         self.launch(output, target, loss, dev)
-        self.fetch(dev, n)
+        self.fetch(dev, n, stream=self.side)
 
     def launch(self, output, target, loss, dev) -> None:
         """Enqueue the metric kernel writing into ``dev`` (capturable in a CUDA graph)."""
         lossf = loss.detach()
         if lossf.dtype != torch.float32:
             lossf = lossf.float()
-        if self.reduce and getattr(self.comm, "backend", "") == "fused":
+        if self.side is not None:
+            out = output.detach()
+            ev = torch.cuda.Event()
+            ev.record()
+            self.side.wait_event(ev)
+            with torch.cuda.stream(self.side):
+                self.comm.metrics(out, target, lossf, dev)
+            for t in (out, target, lossf):
+                t.record_stream(self.side)
+            self._side_dirty = True
+        elif self.reduce and getattr(self.comm, "backend", "") == "fused":
             self.comm.metrics(output.detach(), target, lossf, dev)
         else:
             from . import _ext
@@ -106,17 +122,30 @@ class MetricPipeline:
             if self.reduce and self.comm.world > 1:
                 self.comm.reduce_scalars_(dev[:3], average=True)
 
-    def fetch(self, dev, n: int) -> None:
-        """16-byte D2H copy of a finished (or enqueued) metric vector into the pinned ring + completion event."""
+    def fetch(self, dev, n: int, stream=None) -> None:
+        """16-byte D2H copy of a finished (or enqueued) metric vector into the pinned ring + completion event.
+        ``stream``: the stream the metric kernel was enqueued on (None = the current one, e.g. after a graph replay)."""
         if len(self.pending) >= len(self.ring) - 1:
             self.poll(block_oldest=True)
         i = self.slot
         self.slot = (self.slot + 1) % len(self.ring)
-        self.ring[i].copy_(dev, non_blocking=True)
-        self.d2h_bytes += 16
         ev = torch.cuda.Event()
-        ev.record()
+        if stream is not None:
+            with torch.cuda.stream(stream):
+                self.ring[i].copy_(dev, non_blocking=True)
+                ev.record(stream)
+        else:
+            self.ring[i].copy_(dev, non_blocking=True)
+            ev.record()
+        self.d2h_bytes += 16
         self.pending.append((ev, i, n))
+
+    def join(self) -> None:
+        """Make the current stream wait for metric work enqueued on the side stream (needed before a capture ends and
+        before buffers the kernel reads may be reused)."""
+        if self.side is not None and self._side_dirty:
+            torch.cuda.current_stream().wait_stream(self.side)
+            self._side_dirty = False
 
     def _apply(self, vals, n):
         self.last = (vals[0], vals[1], vals[2])
@@ -185,7 +214,10 @@ class TrainStep:
             self.metrics.push(output, target, loss, images.size(0))
         else:
             self.metrics.launch(output, target, loss, dev)
-        if dev is None:
+        eng = getattr(self.st, "engine", None)
+        if eng is not None and getattr(eng, "bucket_view", False):
+            eng.zero_grads()           # bucket views: ONE memset of the arena; backward then accumulates in place (no pack pass)
+        elif dev is None:
             self.optimizer.zero_grad()
         if nvtx:
             torch.cuda.nvtx.range_pop()
@@ -197,6 +229,7 @@ class TrainStep:
         self.optimizer.step()
         if nvtx:
             torch.cuda.nvtx.range_pop()
+        self.metrics.join()
         eng = getattr(self.st, "engine", None)
         if _POISON and eng is not None and getattr(eng, "_flat", None) is not None and getattr(eng, "fused", False):
             eng.grad_arena().fill_(float("nan"))   # PTD_DEBUG_POISON=1: a stale read of the wire arena shows up as NaN
@@ -244,6 +277,7 @@ class Strategy:
     raw_uint8_loader = False
     cast_params = True          # low precision = cast the model (fp32 masters in FusedSGD); False => autocast
     graph_capable = True        # the train step may be captured into a CUDA graph (--cuda-graph)
+    overlap_optimizer = True    # one backward per step and nothing between backward and step: the update may ride behind each bucket
     epoch_csv: Optional[str] = None
 
     def init_process_group(self, args, local_rank: int, nprocs: int) -> None:
@@ -252,7 +286,11 @@ class Strategy:
         if backend == "nccl":
             kw["device_id"] = torch.device("cuda", local_rank)
         if args.dist_url:
-            dist.init_process_group(backend=backend, init_method=args.dist_url, world_size=nprocs, rank=local_rank, **kw)
+            # multi-node launchers (Slurm) put the GLOBAL rank in args.global_rank (= node_rank * ngpus + gpu, reference
+            # distributed_slurm_main.py:147); local_rank only ever selects the device
+            rank = getattr(args, "global_rank", None)
+            dist.init_process_group(backend=backend, init_method=args.dist_url, world_size=nprocs,
+                                    rank=local_rank if rank is None else int(rank), **kw)
         else:
             dist.init_process_group(backend=backend, **kw)
 
@@ -292,14 +330,16 @@ class Strategy:
     def make_optimizer(self, model, args):
         if args.optimizer == "fused":
             from .ops.fused_sgd import FusedSGD
-            return FusedSGD(model.parameters(), args.lr, momentum=args.momentum, weight_decay=args.weight_decay)
+            return FusedSGD(model.parameters(), args.lr, momentum=args.momentum, weight_decay=args.weight_decay,
+                            overlap_backward=bool(getattr(args, "overlap_optimizer", False)) and self.overlap_optimizer)
         return torch.optim.SGD(model.parameters(), args.lr, momentum=args.momentum, weight_decay=args.weight_decay)
 
     def wrap(self, model, args, device, local_rank):
         from .parallel.ddp import DistributedDataParallel
         wire = args.wire_dtype if device.type == "cuda" else "fp32"
         model = DistributedDataParallel(model, device_ids=[local_rank] if device.type == "cuda" else None,
-                                        comm=self.comm_kind(args, device), wire_dtype=wire, bucket_cap_mb=args.bucket_cap_mb)
+                                        comm=self.comm_kind(args, device), wire_dtype=wire, bucket_cap_mb=args.bucket_cap_mb,
+                                        gradient_as_bucket_view=bool(getattr(args, "bucket_view", False)) and device.type == "cuda")
         self.comm = model.comm
         self.engine = model.engine
         from .utils.dist_ops import set_default_communicator
@@ -370,9 +410,10 @@ class ApexStrategy(Strategy):
 class HorovodStrategy(Strategy):
     """/root/reference/horovod_distributed.py: broadcast_parameters + DistributedOptimizer(compression=fp16)."""
     name = "horovod_distributed"
+    overlap_optimizer = False   # horovod semantics: step() synchronises the handles first, then updates
     cast_params = False         # gradients come back decompressed to fp32 into p.grad: keep fp32 weights + autocast
     # the fusion dispatcher is a host thread: not capturable - unless the static schedule replaces it after the first step
-    graph_capable = os.environ.get("PTD_HVD_STATIC", "0") == "1"
+    graph_capable = os.environ.get("PTD_HVD_STATIC", "1") == "1" and os.environ.get("HOROVOD_AUTOTUNE", "0") != "1"
 
     def init_process_group(self, args, local_rank, nprocs):
         from .parallel import hvd
@@ -407,6 +448,7 @@ class DataParallelStrategy(Strategy):
     shard_batch = False
     reduce_metrics = False
     graph_capable = False       # replica forwards run on host threads across devices
+    overlap_optimizer = False   # one reduce at the end of backward (K5): nothing to ride behind
     epoch_csv = "dataparallel.csv"
 
     def init_process_group(self, args, local_rank, nprocs):
@@ -501,6 +543,58 @@ def main_worker(local_rank: int, nprocs: int, args, strategy: Optional[Strategy]
     _shutdown(st)
 
 
+class _DeviceStepTimer:
+    """Device-timed seconds per training step: one CUDA event per print interval, read after the metric drain has
+    synchronised with the device anyway (no extra stall)."""
+
+    def __init__(self, device):
+        self.enabled = device.type == "cuda"
+        self.prev = None
+        self.prev_i = 0
+
+    def lap(self, i):
+        if not self.enabled:
+            return 0.0, 0
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        ev.synchronize()
+        out = (0.0, 0)
+        if self.prev is not None and i > self.prev_i:
+            n = i - self.prev_i
+            out = (self.prev.elapsed_time(ev) / 1e3 / n, n)
+        self.prev, self.prev_i = ev, i
+        return out
+
+
+def _test_kill_step(st) -> int:
+    """PTD_TEST_KILL_RANK / PTD_TEST_KILL_STEP: failure-injection hook used by the kill-a-rank tests."""
+    r = os.environ.get("PTD_TEST_KILL_RANK")
+    if r is None or int(r) != (st.rank() if st.distributed else 0):
+        return -1
+    return int(os.environ.get("PTD_TEST_KILL_STEP", "3"))
+
+
+def _raise_with_comm_diagnosis(st, err):
+    """A peer that never arrives makes the waiting kernel trap after PTD_COMM_TIMEOUT_MS (csrc/common.cuh) and leaves a status
+    word in host-mapped memory; the CUDA context is gone after that, so every later call fails with an unrelated-looking
+    error.  Turn that into ONE clear message and leave without touching CUDA / the process group again."""
+    comm = getattr(st, "comm", None)
+    status = 0
+    try:
+        status = comm.arena.status() if comm is not None and hasattr(comm, "arena") else 0
+    except Exception:  # noqa: BLE001
+        pass
+    if status:
+        import sys
+        rank = st.rank() if st.distributed else 0
+        sys.stderr.write("[ptd] rank %d: a fused collective timed out waiting for a peer (status 0x%08x, timeout %s ms): a peer process "
+                         "died or hung. Aborting this rank; the launcher tears the job down.\n  original error: %s\n" %
+                         (rank, status, os.environ.get("PTD_COMM_TIMEOUT_MS", "120000"), str(err).splitlines()[0] if str(err) else type(err).__name__))
+        sys.stderr.flush()
+        os._exit(3)
+    raise err
+
+
 def _shutdown(st):
     comm = getattr(st, "comm", None)
     if comm is not None:
@@ -537,17 +631,34 @@ def train(train_loader, model, criterion, optimizer, epoch, st: Strategy, device
     end = time.time()
     t0 = end
     n_img = 0
-    for i, (images, target) in enumerate(pf):
-        data_time.update(time.time() - end)
-        step(images, target)
-        n_img += images.size(0)
-        batch_time.update(time.time() - end)
-        end = time.time()
-        if i % args.print_freq == 0:
-            metrics.drain()
-            if not args.quiet:
-                progress.display(i)
-    metrics.drain()
+    comm = getattr(st, "comm", None)
+    timer = _DeviceStepTimer(device)
+    kill_at = _test_kill_step(st)
+    try:
+        for i, (images, target) in enumerate(pf):
+            data_time.update(time.time() - end)
+            step(images, target)
+            n_img += images.size(0)
+            if not timer.enabled:
+                batch_time.update(time.time() - end)      # CPU: the loop is synchronous, host time is step time
+            end = time.time()
+            if i == kill_at:
+                os.kill(os.getpid(), 9)                    # test hook (tests/test_cpu_failure.py): this rank dies mid-epoch
+            if i % args.print_freq == 0:
+                metrics.drain()
+                # The reference's Time meter was valid because .item() synchronised every iteration
+                # (/root/reference/distributed.py:262,272).  Here nothing blocks the host (under --cuda-graph a step is one
+                # launch), so Time is measured ON THE DEVICE: CUDA events bracket each print interval.
+                dt, n = timer.lap(i)
+                if n:
+                    batch_time.update(dt, n)
+                if comm is not None:
+                    comm.check()                           # a peer that stopped arriving: fail now, not at shutdown
+                if not args.quiet:
+                    progress.display(i)
+        metrics.drain()
+    except RuntimeError as e:
+        _raise_with_comm_diagnosis(st, e)
     if device.type == "cuda":
         torch.cuda.synchronize(device)
     _log_jsonl(args, {"phase": "train", "epoch": epoch, "rank": st.rank() if st.distributed else 0, "images": n_img,

@@ -33,7 +33,8 @@ def sgd_reference_step(p, g, buf, lr, momentum, weight_decay, dampening, nestero
 
 
 class FusedSGD(Optimizer):
-    def __init__(self, params, lr=0.1, momentum=0.0, dampening=0.0, weight_decay=0.0, nesterov=False, flat: Optional[bool] = None):
+    def __init__(self, params, lr=0.1, momentum=0.0, dampening=0.0, weight_decay=0.0, nesterov=False, flat: Optional[bool] = None,
+                 overlap_backward: bool = False):
         if nesterov and (momentum <= 0 or dampening != 0):
             raise ValueError("Nesterov momentum requires a momentum and zero dampening")
         defaults = dict(lr=lr, momentum=momentum, dampening=dampening, weight_decay=weight_decay, nesterov=nesterov)
@@ -43,6 +44,16 @@ class FusedSGD(Optimizer):
         self._hyper = {}            # group index -> (device tensor, cached python tuple)
         self._amp = None            # LossScaler (set by amp.initialize)
         self._want_flat = flat
+        # overlap_backward: in flat mode the update of each gradient bucket is enqueued on the communication stream right
+        # behind that bucket's all-reduce (inside loss.backward()), so after the last gradient only the small tail bucket
+        # remains; step() then only joins.  Contract: exactly one backward per step() and no gradient surgery between them
+        # (the reference loop, /root/reference/distributed.py:267-269).  Inactive under a loss scaler (an overflow found in
+        # a later bucket must be able to cancel the whole step).
+        self._overlap = bool(overlap_backward)
+        self._ov_active = False
+        self._ov_applied = 0
+        self._ov_first = False
+        self._bind_refused = False  # an engine was found but declined (mixed dtypes, other parameter list): do not retry
         self._try_bind()
 
     # ------------------------------------------------------------------ engine binding (flat mode)
@@ -60,6 +71,33 @@ class FusedSGD(Optimizer):
         if eng is None or not getattr(eng, "supports_flat_optimizer", False):
             return
         self._flat = eng.bind_flat_optimizer(self, params)
+        if self._flat is None:
+            self._bind_refused = True
+        elif self._overlap and getattr(eng, "supports_overlap_optimizer", False):
+            eng.set_overlap_optimizer(self)
+
+    # ------------------------------------------------------------------ overlap mode (called by the gradient engine)
+    def _prepare_overlap(self) -> None:
+        """First bucket of a backward pass, on the compute stream: decide whether this step is applied bucket by bucket
+        and push the hyper-parameters to the device before the side stream forks off."""
+        self._ov_applied = 0
+        self._ov_active = self._flat is not None and self._amp is None
+        if self._ov_active:
+            self._ov_first = self._steps == 0
+            self._hyper_tensor(0, self.param_groups[0], self._flat.master.device)
+
+    @torch.no_grad()
+    def _apply_slice(self, off: int, n: int) -> None:
+        """SGD update of flat elements [off, off + n) - the bucket whose all-reduce was just enqueued on this stream."""
+        if not self._ov_active:
+            return
+        fs = self._flat
+        from .. import _ext
+        _ext.note_launch()
+        copy = fs.model_copy[off:off + n] if fs.model_copy is not None else None
+        _ext.lib().fused_sgd_flat(fs.engine.grad_arena()[off:off + n], fs.master[off:off + n], fs.momentum[off:off + n], copy,
+                                  self._hyper[0][0], None, bool(self.param_groups[0]["nesterov"]), self._ov_first)
+        self._ov_applied += n
 
     @property
     def is_flat(self) -> bool:
@@ -94,12 +132,21 @@ class FusedSGD(Optimizer):
                 loss = closure()
         first = self._steps == 0
         amp = self._amp
-        if self._flat is None and first:
-            self._try_bind()      # the engine may have been created after this optimizer (apex order: amp -> DDP)
+        if self._flat is None and not self._bind_refused:
+            # the engine may have been created after this optimizer (apex order: amp -> DDP), and a resumed optimizer
+            # has _steps > 0 before its first step: bind whenever still unbound (existing momentum is carried over)
+            self._try_bind()
         if self._flat is not None:
             fs = self._flat
             fs.engine.wait_for_gradients()
             group = self.param_groups[0]
+            if self._ov_active and self._ov_applied == fs.master.numel():
+                self._ov_applied = 0       # every bucket was updated behind its all-reduce during backward: nothing left to do
+                self._steps += 1
+                return loss
+            if self._ov_applied:
+                raise RuntimeError("FusedSGD(overlap_backward=True): only %d of %d elements were updated during backward" %
+                                   (self._ov_applied, fs.master.numel()))
             hyper = self._hyper_tensor(0, group, fs.master.device)
             if amp is not None:
                 amp.attach_hyper(hyper)

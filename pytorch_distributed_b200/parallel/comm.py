@@ -24,6 +24,9 @@ import torch.distributed as dist
 from . import plan as P
 
 KIND_TWO_SHOT, KIND_ONE_SHOT, KIND_BCAST, KIND_PACK, KIND_REDUCE, KIND_PUSH, KIND_UNPACK = range(7)
+FLAG_PREPACKED = 1        # csrc/collectives.cu kPrepacked: gradients already live in the arena (bucket views)
+# payloads up to this size take the one-shot kernel (one barrier, W x the traffic); tools/comm_bench.py measures the crossover
+ONE_SHOT_MAX_BYTES = int(os.environ.get("PTD_ONESHOT_MAX_BYTES", str(256 << 10)))
 _DT = {torch.float32: "fp32", torch.bfloat16: "bf16", torch.float16: "fp16"}
 _TORCH_DT = {"fp32": torch.float32, "bf16": torch.bfloat16, "fp16": torch.float16}
 _VIEW_NAME = {"fp32": "float32", "bf16": "bfloat16", "fp16": "float16"}
@@ -41,6 +44,8 @@ class Plan:
             offs, total = P.tensor_layout(numels)
         else:
             offs = list(offsets)
+        if total * esz >= (64 << 20) and "PTD_MAX_CTAS" not in os.environ:
+            max_ctas = max(max_ctas, 64)        # >= 64 MB messages: 64 CTAs keep enough multimem requests in flight
         grid = P.choose_grid(total, esz, min(max_ctas, comm.max_blocks))
         self.layout = P.build_layout(numels, comm.world, grid, offs, total)
         self.grid = grid
@@ -54,7 +59,8 @@ class Plan:
         self.segs = torch.from_numpy(raw).to(dev)
         self.calls = torch.zeros(max(grid, 1), dtype=torch.int32, device=dev)
         if data_off_bytes is None:
-            data_off_bytes = comm.alloc(self.region_bytes * (2 if double_buffer else 1))
+            # double_buffer: [staging 0 | staging 1 | result] - the third region receives the one-shot kernel's reduced values
+            data_off_bytes = comm.alloc(self.region_bytes * (3 if double_buffer else 1))
         self.data_off_bytes = data_off_bytes
         self.rank_slot = rank_slot
 
@@ -87,6 +93,7 @@ class FusedCommunicator:
         self._bump = self.header_bytes
         self._next_channel = 0
         self._plans = {}
+        self._side_stream = None
         self._lock = threading.RLock()      # plans / arena offsets may be requested from the hvd dispatcher thread too
         if allow_nvls is None:
             allow_nvls = os.environ.get("PTD_NVLS", "1") != "0"
@@ -107,6 +114,15 @@ class FusedCommunicator:
     # ------------------------------------------------------------------ setup
     def device_of(self, rank_slot: int = 0) -> torch.device:
         return self.device
+
+    @property
+    def side_stream(self) -> "torch.cuda.Stream":
+        """THE communication stream of this communicator (high priority): gradient buckets, the deferred BN-buffer
+        broadcast and the metric all-reduce are all enqueued here, in the same order on every rank, so none of their
+        cross-GPU waits sits on the compute stream."""
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream(device=self.device, priority=-1)
+        return self._side_stream
 
     def _gather_obj(self, obj):
         out = [None] * self.world
@@ -221,11 +237,13 @@ class FusedCommunicator:
     def check(self) -> None:
         st = self.arena.status()
         if st:
-            raise RuntimeError("fused collective timed out waiting for a peer (status 0x%08x)" % st)
+            raise RuntimeError("fused collective timed out waiting for a peer (status 0x%08x, rank %d of %d): a peer process died "
+                               "or hung" % (st, self.rank, self.world))
 
     # ------------------------------------------------------------------ launches
     def run(self, plan: Plan, tensors: List[torch.Tensor], kind: int, channel: int, scale: float = 1.0, writeback: bool = True,
-            root: int = 0, check_inf: bool = False, nvls: Optional[bool] = None, rank_slot: int = 0) -> None:
+            root: int = 0, check_inf: bool = False, nvls: Optional[bool] = None, rank_slot: int = 0, prepacked: bool = False,
+            result_off_bytes: int = -1) -> None:
         use_nvls = self.nvls if nvls is None else (nvls and self.nvls)
         if len(tensors) > self._C.MAX_PTRS:
             raise RuntimeError("too many tensors for one plan launch")
@@ -233,7 +251,7 @@ class FusedCommunicator:
         self.arena.launch_plan(channel, rank_slot, kind, P.WIRE_CODES[plan.wire], use_nvls, plan.grid, tensors,
                                plan.seg_begin.data_ptr(), plan.segs.data_ptr(), plan.data_off_bytes, plan.block_elems,
                                plan.calls.data_ptr(), self.found_inf.data_ptr() if check_inf else 0, float(scale), bool(writeback),
-                               int(root))
+                               int(root), FLAG_PREPACKED if prepacked else 0, int(result_off_bytes))
 
     def _cached_plan(self, key, tensors, wire, double_buffer, max_ctas=None):
         with self._lock:
@@ -255,7 +273,7 @@ class FusedCommunicator:
         if wire is None:
             wire = "fp32" if all(t.dtype == torch.float32 for t in tensors) else _DT[tensors[0].dtype]
         nbytes = sum(t.numel() for t in tensors) * P.WIRE_BYTES[wire]
-        one_shot = nbytes <= (256 << 10)
+        one_shot = nbytes <= ONE_SHOT_MAX_BYTES
         key = ("ar", one_shot, wire, self._sig(tensors))
         pl = self._cached_plan(key, tensors, wire, double_buffer=one_shot)
         scale = 1.0 / self.world if average else 1.0

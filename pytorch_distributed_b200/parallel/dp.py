@@ -52,11 +52,6 @@ class LocalCommunicator:
         self.nvls = bool(self.arena.has_multicast)
         self.header_bytes = P.round_up(self._C.SIGNAL_PAD_BYTES, 128 << 10)
         self._bump = self.header_bytes
-        # peer access for tensors that live in the regular caching allocator (scatter / gather kernels)
-        for a in self.devices:
-            for b in self.devices:
-                if a != b:
-                    torch.cuda.can_device_access_peer(a, b)
 
     def device_of(self, rank_slot: int = 0) -> torch.device:
         return torch.device("cuda", self.devices[rank_slot])
@@ -156,6 +151,20 @@ class _Gather(torch.autograd.Function):
         return (None,) + tuple(grads)
 
 
+class _ArmReduce(torch.autograd.Function):
+    """Identity whose backward arms the end-of-backward gradient hand-over (single-device engine: there is no gather node)."""
+
+    @staticmethod
+    def forward(ctx, engine, x):
+        ctx.engine = engine
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, grad):
+        ctx.engine._arm_reduce()
+        return None, grad
+
+
 class DataParallelEngine:
     supports_flat_optimizer = True
 
@@ -252,7 +261,8 @@ class DataParallelEngine:
                     root_stream.wait_event(ev)
         with torch.cuda.device(self.root_device):
             root_grads = [p.grad for p in self.rparams[0]]
-            self.grads.launch(KIND_REDUCE, 0, writeback=self.writeback, tensors=root_grads)
+            if self.world > 1:          # world == 1: the pack above already left this device's gradients in the arena
+                self.grads.launch(KIND_REDUCE, 0, writeback=self.writeback, tensors=root_grads)
             ev = torch.cuda.Event()
             ev.record(root_stream)
         self._grads_ready_event = ev
@@ -315,7 +325,12 @@ class DataParallel(nn.Module):
         if eng is None or eng.world == 0:
             return self.module(x)
         if eng.world == 1:
-            return self.module(x)
+            # one device: no scatter / broadcast / gather, but a flat optimizer still reads the gradient ARENA, so backward
+            # must end with the pack that fills it (without it the optimizer would step on stale memory)
+            out = self.module(x)
+            if torch.is_grad_enabled() and out.requires_grad:
+                out = _ArmReduce.apply(eng, out)
+            return out
         for m in eng.modules[1:]:
             m.train(self.module.training)
         eng.broadcast_values()

@@ -228,10 +228,11 @@ class _FusionEngine:
         self.enabled = True
         self.queue = None
         self.thread = None
-        # Static schedule (PTD_HVD_STATIC=1): group composition only depends on hook order and sizes, so after the first complete
-        # step the recorded groups are frozen and the hooks launch them directly - no queue, no dispatcher thread, and the
-        # step becomes capturable in a CUDA graph.  Until then (and by default) requests go through the C++ fusion queue.
-        self._static_wanted = os.environ.get("PTD_HVD_STATIC", "0") == "1"
+        # Static schedule (default; PTD_HVD_STATIC=0 keeps the queue): group composition only depends on hook order and sizes,
+        # so after the first complete step the recorded groups are frozen and the hooks launch them directly - no queue, no
+        # dispatcher thread, and the step becomes capturable in a CUDA graph.  Until then requests go through the C++ fusion
+        # queue, whose groups close at the cycle budget (so the very first steps overlap with backward as well).
+        self._static_wanted = os.environ.get("PTD_HVD_STATIC", "1") == "1"
         self._trace = []            # groups (tuples of parameter indices) launched by the dispatcher during the current step
         self._schedule = None       # frozen trace
         self._group_of: Dict[int, int] = {}
@@ -241,9 +242,17 @@ class _FusionEngine:
         if comm.world > 1 or self.fused:
             C = _ext.lib() if self.fused or _ext.available() else None
             if C is not None:
-                self.queue = C.FusionQueue(int(fusion_threshold_mb * (1 << 20)), float(cycle_time_ms))
+                # horovod closes a fusion group every HOROVOD_CYCLE_TIME ms; here the tick is a byte budget (same groups on
+                # every rank without a negotiation round): cycle_time_ms x PTD_HVD_BYTES_PER_MS (default 2 MiB/ms => 10 MiB)
+                per_ms = float(os.environ.get("PTD_HVD_BYTES_PER_MS", 2 << 20))
+                self.cycle_bytes = int(os.environ.get("PTD_HVD_CYCLE_BYTES", max(1.0, cycle_time_ms) * per_ms))
+                self.queue = C.FusionQueue(int(fusion_threshold_mb * (1 << 20)), float(cycle_time_ms), self.cycle_bytes)
+                self._timeline_path = os.environ.get("HOROVOD_TIMELINE", "")
+                if self._timeline_path:
+                    self.queue.enable_timeline(True)
+        self._tuner = _Autotuner(self) if (self.queue is not None and os.environ.get("HOROVOD_AUTOTUNE", "0") == "1") else None
         if self.fused:
-            self.stream = torch.cuda.Stream(device=comm.device, priority=-1)
+            self.stream = comm.side_stream
             self.channel = comm.new_channel()
         if self.queue is not None:
             self.thread = threading.Thread(target=self._dispatch_loop, name="ptd-hvd-cycle", daemon=True)
@@ -273,8 +282,8 @@ class _FusionEngine:
             if param.is_cuda:
                 ev = torch.cuda.Event()
                 ev.record()
-            h = self.queue.enqueue(self.named[i][0], self._wire_bytes(param), i)
-            with _lock:
+            with _lock:        # enqueue may close the group and wake the dispatcher: the handle must be registered first
+                h = self.queue.enqueue(self.named[i][0], self._wire_bytes(param), i)
                 self._handles[h] = i
                 self._events[h] = ev
         return hook
@@ -343,6 +352,7 @@ class _FusionEngine:
                 self._launch_group(handles)
             except Exception as e:  # noqa: BLE001 - surfaced by synchronize()
                 self._error = e
+                self.queue.wake()
             self.queue.mark_done(handles)
 
     _stop = False
@@ -361,21 +371,43 @@ class _FusionEngine:
         if self.queue is None:
             return
         self.queue.flush()
-        while self.queue.pending() > 0:
-            if self._error is not None:
+        while not self.queue.wait_idle(1000.0):      # condition variable in C++, GIL released: no polling
+            if self._error is not None or self._stop:
                 break
-            time.sleep(0.0002)
         if self._error is not None:
             e, self._error = self._error, None
             raise e
         if self.fused:
             torch.cuda.current_stream().wait_stream(self.stream)
         trace, self._trace = self._trace, []
+        if self._tuner is not None and not self._tuner.done:
+            self._tuner.step_done()                 # HOROVOD_AUTOTUNE: try the next cycle budget / pick the winner
+            return
         if self._static_wanted and trace and sorted(i for g in trace for i in g) == list(range(len(self.params))):
             self._freeze(trace)                     # a complete step (every parameter exactly once): freeze its grouping
 
+    def write_timeline(self):
+        """HOROVOD_TIMELINE=<file>: chrome-trace JSON of the fusion queue (one slice per tensor from enqueue to dispatch,
+        grouped by fusion group) - the part of horovod's timeline that exists here (there is no negotiation phase)."""
+        path = getattr(self, "_timeline_path", "")
+        if not path or self.queue is None:
+            return
+        import json
+        recs = self.queue.timeline()
+        if not recs:
+            return
+        evs = [{"name": n, "cat": "fusion", "ph": "X", "ts": t0, "dur": max(t1 - t0, 0.01), "pid": self.comm.rank, "tid": int(g) % 8,
+                "args": {"bytes": b, "group": g}} for (n, b, g, t0, t1) in recs]
+        base, ext = os.path.splitext(path)
+        with open("%s.rank%d%s" % (base, self.comm.rank, ext or ".json"), "w") as f:
+            json.dump({"traceEvents": evs, "stats": self.queue.stats()}, f)
+
     def close(self):
         self._stop = True
+        try:
+            self.write_timeline()
+        except Exception:  # noqa: BLE001
+            pass
         if self.queue is not None:
             self.queue.shutdown()
         if self.thread is not None and self.thread.is_alive() and threading.current_thread() is not self.thread:
@@ -384,6 +416,70 @@ class _FusionEngine:
         for h in self._hooks:
             h.remove()
         self._hooks = []
+
+
+class _Autotuner:
+    """HOROVOD_AUTOTUNE=1: pick the fusion cycle budget by measurement.
+
+    Horovod tunes fusion threshold and cycle time with Bayesian optimisation over many steps; here the only knob that
+    changes the schedule is the byte budget at which a group closes, so a short deterministic sweep is enough: every
+    candidate runs ``HOROVOD_AUTOTUNE_STEPS_PER_SAMPLE`` steps (after one settling step) timed with CUDA events, the
+    per-candidate means are max-reduced over the ranks (every rank must pick the same winner), the best budget is set
+    and - if the static schedule is enabled - the next step's groups are frozen.  All ranks switch candidates at the same
+    step counts, so the groups stay identical across ranks throughout.
+    """
+
+    def __init__(self, engine, candidates_mb=(2, 4, 8, 16, 32, 64)):
+        self.e = engine
+        self.cands = [int(c * (1 << 20)) for c in candidates_mb]
+        self.per = max(1, int(os.environ.get("HOROVOD_AUTOTUNE_STEPS_PER_SAMPLE", "5")))
+        self.idx, self.count, self.done = 0, -1, False
+        self.times = [0.0] * len(self.cands)
+        self.ev = None
+        self.log = os.environ.get("HOROVOD_AUTOTUNE_LOG", "")
+        engine.queue.set_cycle_bytes(self.cands[0])
+
+    def _now(self):
+        if self.e.fused:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            return ev
+        return time.perf_counter()
+
+    def _elapsed_ms(self, a, b):
+        if self.e.fused:
+            b.synchronize()
+            return a.elapsed_time(b)
+        return (b - a) * 1e3
+
+    def step_done(self):
+        now = self._now()
+        if self.count >= 0 and self.ev is not None:        # count == -1: the settling step after a switch is not timed
+            self.times[self.idx] += self._elapsed_ms(self.ev, now)
+        self.ev = now
+        self.count += 1
+        if self.count < self.per:
+            return
+        self.times[self.idx] /= self.per
+        self.idx += 1
+        self.count, self.ev = -1, None
+        if self.idx < len(self.cands):
+            self.e.queue.set_cycle_bytes(self.cands[self.idx])
+            return
+        t = torch.tensor(self.times, dtype=torch.float64, device=self.e.comm.device if self.e.fused else "cpu")
+        if dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        best = int(torch.argmin(t).item())
+        self.e.cycle_bytes = self.cands[best]
+        self.e.queue.set_cycle_bytes(self.cands[best])
+        self.done = True
+        if self.e.comm.rank == 0:
+            msg = "[hvd autotune] cycle budget MiB -> ms/step: %s; picked %d MiB" % (
+                ", ".join("%d: %.3f" % (c >> 20, x) for c, x in zip(self.cands, t.tolist())), self.cands[best] >> 20)
+            print(msg, flush=True)
+            if self.log:
+                with open(self.log, "a") as f:
+                    f.write(msg + "\n")
 
 
 def DistributedOptimizer(optimizer, named_parameters=None, compression=Compression.none, backward_passes_per_step: int = 1,

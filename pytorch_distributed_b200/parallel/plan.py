@@ -87,12 +87,23 @@ def build_layout(numels: Sequence[int], world: int, grid: int, offsets: Sequence
 
 
 def compute_buckets(numels: Sequence[int], elem_bytes: int, cap_bytes: int, first_cap_bytes: int | None = None,
-                    max_tensors: int = 256) -> List[List[int]]:
+                    max_tensors: int = 256, tail_cap_bytes: int | None = None) -> List[List[int]]:
     """Greedy size-capped bucket assignment over tensors in the given (gradient-ready) order.
 
     Mirrors torch's reducer defaults (first bucket 1 MiB so communication starts early, then ``cap_bytes``); a bucket
     is also closed when it holds ``max_tensors`` tensors (pointer pack limit of one kernel launch).
+    ``tail_cap_bytes``: the LAST bucket is the only one whose all-reduce cannot hide behind backward compute - it is on
+    the critical path between the last gradient and the optimizer - so the final tensors (as many as fit in
+    ``tail_cap_bytes``) are split off into their own small bucket.
     """
+    if tail_cap_bytes is not None and len(numels) > 1:
+        k, acc = len(numels), 0
+        while k > 1 and acc + int(numels[k - 1]) * elem_bytes <= tail_cap_bytes and len(numels) - k < max_tensors:
+            k -= 1
+            acc += int(numels[k]) * elem_bytes
+        if 0 < k < len(numels):
+            head = compute_buckets(numels[:k], elem_bytes, cap_bytes, first_cap_bytes, max_tensors)
+            return head + [list(range(k, len(numels)))]
     buckets, cur, cur_bytes = [], [], 0
     cap = first_cap_bytes if first_cap_bytes is not None else cap_bytes
     for i, n in enumerate(numels):

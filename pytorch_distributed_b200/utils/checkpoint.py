@@ -56,6 +56,11 @@ def load_checkpoint(path: str, module: torch.nn.Module, optimizer=None, map_loca
                 own[k].copy_(v.to(own[k].dtype))
         # low-precision model copies are derived from fp32 master weights: the masters must get the checkpoint too,
         # otherwise the next optimizer step would regenerate the model from stale masters
+        # masters that do not exist yet (optimizer binds lazily at its first step) are seeded from the stash left by
+        # amp.cast_model: point it at the checkpoint's fp32 values, otherwise the first step would discard the checkpoint
+        for name, p in module.named_parameters():
+            if getattr(p, "_ptd_master_init", None) is not None and name in sd:
+                p._ptd_master_init = sd[name].detach().to(device=p.device, dtype=torch.float32).reshape(p.shape).clone()
         if engine is not None and hasattr(engine, "master_params"):
             idx = {id(p): i for i, p in enumerate(engine.params)}
             masters = engine.master_params()

@@ -76,6 +76,31 @@ def test_slurm_entrypoint_fake_env(tmp_path):
     assert os.path.exists(tmp_path / "distributed.csv")
 
 
+def test_slurm_two_nodes_global_rank(tmp_path):
+    """Two fake Slurm tasks (one 'node' each, one worker per node): the process group must be built from the GLOBAL rank
+    (node_rank * ngpus + gpu), not the local one - with local ranks both tasks would register as rank 0 and hang."""
+    procs = []
+    for node in (0, 1):
+        env = _env({"SLURM_PROCID": str(node), "SLURM_NPROCS": "2", "SLURM_JOBID": "78"})
+        d = tmp_path / ("node%d" % node)
+        d.mkdir()
+        cmd = [sys.executable, os.path.join(ROOT, "distributed_slurm_main.py")] + COMMON + \
+              ["--world-size", "1", "--dist-file", str(tmp_path / "rdzv2"), "--checkpoint-dir", str(d)]
+        procs.append(subprocess.Popen(cmd, env=env, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    outs = []
+    for p in procs:
+        try:
+            o, e = p.communicate(timeout=600)
+        except subprocess.TimeoutExpired:
+            for q in procs:
+                q.kill()
+            raise
+        assert p.returncode == 0, o[-2000:] + "\n" + e[-3000:]
+        outs.append(o)
+    _check_output("\n".join(outs), 2, tmp_path / "node0")
+    assert not os.path.exists(tmp_path / "node1" / "checkpoint.pth.tar")      # only global rank 0 saves (Q11)
+
+
 def test_dataparallel_cpu_passthrough(tmp_path):
     out = _run([sys.executable, os.path.join(ROOT, "dataparallel.py")] + COMMON + ["--checkpoint-dir", str(tmp_path)])
     assert " * Acc@1" in out and os.path.exists(tmp_path / "dataparallel.csv")

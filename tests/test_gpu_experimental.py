@@ -2,9 +2,12 @@
 their PyTorch emulation on CPU, not yet run on hardware.  They are opt-in (PTD_TEST_EXPERIMENTAL=1) so that the regular GPU
 tier only contains hardware-validated paths; enable them first thing in the next GPU session."""
 import os
+import sys
 
 import pytest
 import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(os.environ.get("PTD_TEST_EXPERIMENTAL", "0") != "1", reason="opt-in: PTD_TEST_EXPERIMENTAL=1")]
@@ -45,19 +48,52 @@ def test_bn_backward2_matches_emulation(dt, relu, shape):
     assert (dx.float() - dx1.float()).abs().max().item() <= tol * scale
 
 
-def test_resnet50_step_with_split_residual_gradients():
-    """Whole model: PTD_SPLIT_RESGRAD path vs the default path, same weights and batch (bf16, fused kernels)."""
+def _bf16_model_and_batch(n=32, size=96, classes=64):
+    from _oracle import small_resnet
+    from pytorch_distributed_b200.parallel.amp import cast_model
+    dev = torch.device("cuda", 0)
+    base = cast_model(small_resnet(classes).to(dev).to(memory_format=torch.channels_last), torch.bfloat16)
+    for p in base.parameters():                      # drop the fp32 stash: the oracle must see the bf16-rounded weights
+        if hasattr(p, "_ptd_master_init"):
+            del p._ptd_master_init
+    torch.manual_seed(1)
+    x = torch.randn(n, 3, size, size, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
+    y = torch.randint(0, classes, (n,), device=dev)
+    return base, x, y
+
+
+def _variant_vs_oracle(**flags):
+    import copy
+    from _oracle import compare, fp32_oracle, model_flags, step
+    base, x, y = _bf16_model_and_batch()
+    oracle = fp32_oracle(base, x, y)
+    default = step(copy.deepcopy(base).train(), x, y)
+    with model_flags(**flags):
+        variant = step(copy.deepcopy(base).train(), x, y)
+    torch.cuda.synchronize()
+    assert all(torch.isfinite(g).all() for g in variant[1].values())
+    bad = compare(variant, default, oracle)
+    assert not bad, "error vs the fp32 oracle (name, variant, default path): %s" % (bad[:8],)
+
+
+def test_split_residual_gradients_vs_fp32_oracle():
+    """Whole (shallow) bottleneck ResNet step: SPLIT_RESGRAD vs the default path, both judged against plain fp32 PyTorch."""
+    _variant_vs_oracle(SPLIT_RESGRAD=True)
+
+
+def test_resnet50_step_with_split_residual_gradients_forward_identical():
+    """The split only changes backward: the forward output must be bit-identical on the full-depth model."""
     import copy
     import pytorch_distributed_b200.models.resnet as R
     from pytorch_distributed_b200.models import create_model
+    from pytorch_distributed_b200.parallel.amp import cast_model
     torch.manual_seed(0)
     dev = torch.device("cuda", 0)
-    from pytorch_distributed_b200.parallel.amp import cast_model
     base = cast_model(create_model("resnet50", num_classes=100).to(dev).to(memory_format=torch.channels_last), torch.bfloat16)
     x = torch.randn(16, 3, 96, 96, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
     y = torch.randint(0, 100, (16,), device=dev)
     outs = []
-    for split in (False, False, True):          # the default path twice: its own run-to-run noise (atomics order) calibrates the bound
+    for split in (False, True):
         m = copy.deepcopy(base).train()
         R.SPLIT_RESGRAD = split
         try:
@@ -65,16 +101,10 @@ def test_resnet50_step_with_split_residual_gradients():
             torch.nn.functional.cross_entropy(out.float(), y).backward()
         finally:
             R.SPLIT_RESGRAD = False
-        outs.append((out.float(), {n: p.grad.float() for n, p in m.named_parameters()}))
-    torch.cuda.synchronize()
-    assert torch.allclose(outs[0][0], outs[2][0], rtol=2e-2, atol=2e-2)
-
-    def worst(a, b):
-        return max(((a[n] - b[n]).abs().max() / (a[n].abs().max() + 1e-12)).item() for n in a)
-
-    noise = worst(outs[0][1], outs[1][1])
-    diff = worst(outs[0][1], outs[2][1])
-    assert diff <= max(5 * noise, 2e-2), (diff, noise)
+        outs.append(out.float())
+        assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
+    # the BN statistics are reduced with atomics (order varies run to run): equal up to that noise
+    assert torch.allclose(outs[0], outs[1], rtol=5e-2, atol=5e-2)
 
 
 @pytest.mark.parametrize("shape", [(4, 3, 64, 64), (2, 3, 75, 91), (16, 3, 224, 224)])
@@ -121,29 +151,12 @@ def test_stem_gemm_path_matches_cudnn_path():
         assert err < 3e-2, (n, err)
 
 
-def test_resnet50_step_with_stem_gemm():
-    import copy
-    import pytorch_distributed_b200.models.resnet as R
-    from pytorch_distributed_b200.models import create_model
-    torch.manual_seed(0)
-    dev = torch.device("cuda", 0)
-    from pytorch_distributed_b200.parallel.amp import cast_model
-    base = cast_model(create_model("resnet50", num_classes=100).to(dev).to(memory_format=torch.channels_last), torch.bfloat16)
-    x = torch.randn(16, 3, 128, 128, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
-    y = torch.randint(0, 100, (16,), device=dev)
-    outs = []
-    for flag in (False, True):
-        m = copy.deepcopy(base).train()
-        R.STEM_GEMM = flag
-        try:
-            out = m(x)
-            torch.nn.functional.cross_entropy(out.float(), y).backward()
-        finally:
-            R.STEM_GEMM = False
-        outs.append((out.float(), m.conv1.weight.grad.float()))
-    torch.cuda.synchronize()
-    assert (outs[0][0] - outs[1][0]).abs().max().item() < 0.1 * outs[0][0].abs().max().item()
-    assert (outs[0][1] - outs[1][1]).abs().max().item() < 0.1 * outs[0][1].abs().max().item()
+def test_stem_gemm_vs_fp32_oracle():
+    _variant_vs_oracle(STEM_GEMM=True)
+
+
+def test_split_and_stem_gemm_vs_fp32_oracle():
+    _variant_vs_oracle(STEM_GEMM=True, SPLIT_RESGRAD=True)
 
 
 @pytest.mark.parametrize("graph", [False, True])

@@ -62,6 +62,45 @@ def test_dataparallel_single_gpu(tmp_path):
     assert " * Acc@1" in out and os.path.exists(tmp_path / "dataparallel.csv")
 
 
+def test_dataparallel_single_gpu_applies_gradients():
+    """DataParallel over ONE device with the flat FusedSGD: the optimizer reads the gradient arena, which only the
+    end-of-backward pack fills - weights must move and the loss on a fixed batch must go down."""
+    from pytorch_distributed_b200.models import create_model
+    from pytorch_distributed_b200.ops.fused_sgd import FusedSGD
+    from pytorch_distributed_b200.parallel.dp import DataParallel
+    torch.manual_seed(0)
+    dev = torch.device("cuda", 0)
+    model = create_model("resnet18", num_classes=10).to(dev).to(memory_format=torch.channels_last)
+    dp = DataParallel(model, device_ids=[0])
+    opt = FusedSGD(dp.parameters(), lr=0.05, momentum=0.9)
+    assert opt.is_flat
+    x = torch.randn(16, 3, 64, 64, device=dev).contiguous(memory_format=torch.channels_last)
+    y = torch.randint(0, 10, (16,), device=dev)
+    w0 = model.fc.weight.detach().clone()
+    losses = []
+    for _ in range(6):
+        opt.zero_grad()
+        loss = torch.nn.functional.cross_entropy(dp(x), y)
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert not torch.equal(w0, model.fc.weight.detach()), "weights did not move"
+    assert losses[-1] < losses[0], losses
+
+
+@pytest.mark.parametrize("flags", [["--bucket-view"], ["--no-overlap-optimizer"], ["--bucket-view", "--cuda-graph"]])
+def test_distributed_py_engine_modes_match_default(tmp_path, flags):
+    """gradient_as_bucket_view (in-place accumulation into the arena, K1 without a pack pass) and the non-overlapped optimizer
+    must reproduce the default trajectory (same seed, same data)."""
+    outs = []
+    for extra in ([], flags):
+        args = COMMON + ["--checkpoint-dir", str(tmp_path), "--seed", "5", "--no-fused-bn"] + extra
+        outs.append(_losses(_run([sys.executable, os.path.join(ROOT, "distributed.py")] + args)))
+    assert len(outs[0]) == len(outs[1]) == 8
+    for a, b in zip(outs[0][:5], outs[1][:5]):
+        assert abs(a - b) <= 0.05 * max(1.0, abs(a)), (outs[0], outs[1])
+
+
 def test_evaluate_only(tmp_path):
     out = _run([sys.executable, os.path.join(ROOT, "distributed.py")] + COMMON + ["-e", "--checkpoint-dir", str(tmp_path)])
     assert "Epoch:" not in out and " * Acc@1" in out
