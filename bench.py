@@ -199,7 +199,8 @@ def run_own(a):
     losses, top1, top5 = AverageMeter("Loss"), AverageMeter("Acc@1"), AverageMeter("Acc@5")
     metrics = driver.MetricPipeline(getattr(st, "comm", None), device, (losses, top1, top5), reduce=True)
 
-    use_graph = (not a.no_cuda_graph) and st.graph_capable and getattr(getattr(st, "comm", None), "backend", "") == "fused"
+    use_graph = ((not a.no_cuda_graph) and st.graph_capable and getattr(getattr(st, "comm", None), "backend", "") == "fused"
+                 and hasattr(optimizer, "refresh_hyper"))
     step = driver.TrainStep(st, model, criterion, optimizer, metrics, use_graph=use_graph, warmup=2)   # captured inside warm-up
 
     model.train()

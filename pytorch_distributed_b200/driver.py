@@ -626,7 +626,15 @@ def train(train_loader, model, criterion, optimizer, epoch, st: Strategy, device
     step = getattr(st, "_train_step", None)
     if step is None or step.model is not model:
         fused = getattr(getattr(st, "comm", None), "backend", "") == "fused"     # library collectives are not captured
-        step = st._train_step = TrainStep(st, model, criterion, optimizer, metrics, use_graph=args.cuda_graph and st.graph_capable and fused)
+        # a captured torch.optim.SGD step bakes the Python-float lr into the graph (the x0.1 decay at epochs 30/60 would be
+        # ignored on replay): capture only with an optimizer whose hyper-parameters live on the device
+        dev_hyper = hasattr(optimizer, "refresh_hyper")
+        if args.cuda_graph and not (st.graph_capable and fused and dev_hyper) and not args.quiet and (not st.distributed or st.rank() == 0):
+            print("=> --cuda-graph ignored: %s" % ("entrypoint is not capturable" if not st.graph_capable else
+                                                  "library collectives are not captured" if not fused else
+                                                  "--optimizer torch keeps lr on the host"))
+        step = st._train_step = TrainStep(st, model, criterion, optimizer, metrics,
+                                          use_graph=args.cuda_graph and st.graph_capable and fused and dev_hyper)
     step.metrics = metrics
     end = time.time()
     t0 = end

@@ -144,3 +144,24 @@ def test_metric_pipeline_and_train_step_cpu():
         losses.append(meters[0].val)
     mp.drain()
     assert step.graph is None and losses[-1] < losses[0] * 0.5 and meters[2].val == 100.0 and meters[0].count == 80
+
+
+def test_pretrained_loads_local_torchvision_state_dict(tmp_path, monkeypatch):
+    """--pretrained (reference distributed.py:134-136): a torchvision-format state dict found locally loads into the native ResNet."""
+    import torch
+    import torchvision
+    from pytorch_distributed_b200.models import create_model
+    tv = torchvision.models.resnet18()
+    f = tmp_path / "resnet18-deadbeef.pth"
+    torch.save(tv.state_dict(), f)
+    monkeypatch.setenv("PTD_PRETRAINED_DIR", str(tmp_path))
+    m = create_model("resnet18", pretrained=True)
+    for (n1, a), (n2, b) in zip(tv.state_dict().items(), m.state_dict().items()):
+        assert n1 == n2 and torch.equal(a, b), n1
+    m10 = create_model("resnet18", pretrained=True, num_classes=10)      # other class count: trunk only
+    assert torch.equal(m10.conv1.weight, tv.conv1.weight) and m10.fc.weight.shape[0] == 10
+    monkeypatch.delenv("PTD_PRETRAINED_DIR")
+    monkeypatch.setenv("TORCH_HOME", str(tmp_path / "empty"))
+    import pytest
+    with pytest.raises(RuntimeError, match="no local weights"):
+        create_model("resnet34", pretrained=True)

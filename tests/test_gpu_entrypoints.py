@@ -100,7 +100,7 @@ crit = torch.nn.CrossEntropyLoss()
 o_ref = torch.optim.SGD(ref.parameters(), lr=0.05, momentum=0.9, weight_decay=1e-4)
 o_own = FusedSGD(own.parameters(), lr=0.05, momentum=0.9, weight_decay=1e-4)
 assert o_own.is_flat
-for it in range(3):
+for it in range(6):      # iterations 0-1 eager (replica threads), 2 captures the per-replica CUDA graphs, 3-5 replay them
     x = torch.randn(8 * n, 3, 64, 64, device="cuda:0"); y = torch.randint(0, 10, (8 * n,), device="cuda:0")
     with torch.no_grad():
         for a, b in zip(ref.module.parameters(), own.module.parameters()): a.copy_(b)
@@ -119,6 +119,12 @@ for it in range(3):
         g = arena[off:off + b.numel()].view_as(a)
         assert torch.allclose(g, a.grad, rtol=1e-3, atol=1e-6), (it, nm, (g - a.grad).abs().max().item(), a.grad.abs().max().item())
         assert torch.allclose(a, b, rtol=1e-4, atol=1e-6), (it, nm, (a - b).abs().max().item())
+assert own._graphed is not None and len(own._graphed) == n, "replicas were not graphed"
+# eval / other batch size fall back to the eager forward
+own.eval()
+with torch.no_grad():
+    e = own(torch.randn(3 * n, 3, 64, 64, device="cuda:0"))
+assert e.shape[0] == 3 * n and torch.isfinite(e).all()
 print("DP-PARITY-OK")
 '''
 
