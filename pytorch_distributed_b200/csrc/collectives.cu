@@ -209,6 +209,14 @@ __global__ void __launch_bounds__(kThreads) fused_allreduce_kernel(const __grid_
   const bool prepacked = (a.flags & kPrepacked) != 0;      // gradients are bucket views: autograd wrote them into the arena
   const bool rescale = prepacked && a.scale != 1.0f;
   if (!prepacked) pack_block<W>(pk, a, local);
+  if (c.world == 1 && !a.found_inf && !rescale) {
+    // single rank: the "reduction" is the packed arena itself - no flags, no second pass over the data
+    if (a.writeback) {
+      __syncthreads();
+      unpack_block<W>(pk, a, local, false);
+    }
+    return;
+  }
   block_barrier(c, seq);
 
   constexpr int kUnitElems = 16 / sizeof(W);

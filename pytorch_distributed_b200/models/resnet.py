@@ -27,11 +27,13 @@ FUSED_CONV1X1 = _os.environ.get("PTD_FUSED_CONV1X1", "1") == "1"
 # A block's output has two consumers (the next block's first conv and its skip connection).  With SPLIT_RESGRAD the last
 # BNAct of a block hands out two aliases of its output, so the two gradients reach its backward separately and are
 # summed inside the BN-backward reduction pass (csrc/bn_act.cu: bn_act_backward2) instead of by an autograd add:
-# 7 instead of 9 tensor passes over the widest activations.  Opt-in until it has been timed on hardware.
-SPLIT_RESGRAD = _os.environ.get("PTD_SPLIT_RESGRAD", "0") == "1"
+# 7 instead of 9 tensor passes over the widest activations, -0.8 ms of 22 per step (profiles/bench_r2.md).
+# PTD_SPLIT_RESGRAD=0 restores the autograd add.
+SPLIT_RESGRAD = _os.environ.get("PTD_SPLIT_RESGRAD", "1") == "1"
 # Stem 7x7 convolution as im2col + the tcgen05 GEMM with fused BN statistics instead of cuDNN's legacy C_in = 3 kernels
-# (ops/stem_conv.py).  Opt-in until it has been timed on hardware.
-STEM_GEMM = _os.environ.get("PTD_STEM_GEMM", "0") == "1"
+# (ops/stem_conv.py): cuDNN fprop 1.60 ms + wgrad 0.92 ms -> im2col 0.55 + GEMM 0.30 + wgrad GEMM 0.27 ms, -1.4 ms per step.
+# PTD_STEM_GEMM=0 restores cuDNN.
+STEM_GEMM = _os.environ.get("PTD_STEM_GEMM", "1") == "1"
 
 
 def _pair(x):

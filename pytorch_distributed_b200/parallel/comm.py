@@ -36,7 +36,7 @@ class Plan:
     """Device-resident segment tables + the arena range of one fused collective."""
 
     def __init__(self, comm: "FusedCommunicator", numels: Sequence[int], wire: str, max_ctas: int, double_buffer: bool,
-                 offsets=None, total=None, data_off_bytes: Optional[int] = None, rank_slot: int = 0):
+                 offsets=None, total=None, data_off_bytes: Optional[int] = None, rank_slot: int = 0, bytes_per_cta: int = 256 << 10):
         self.comm = comm
         self.wire = wire
         esz = P.WIRE_BYTES[wire]
@@ -46,7 +46,7 @@ class Plan:
             offs = list(offsets)
         if total * esz >= (64 << 20) and "PTD_MAX_CTAS" not in os.environ:
             max_ctas = max(max_ctas, 64)        # >= 64 MB messages: 64 CTAs keep enough multimem requests in flight
-        grid = P.choose_grid(total, esz, min(max_ctas, comm.max_blocks))
+        grid = P.choose_grid(total, esz, min(max_ctas, comm.max_blocks), bytes_per_cta)
         self.layout = P.build_layout(numels, comm.world, grid, offs, total)
         self.grid = grid
         self.block_elems = self.layout.block_elems

@@ -123,22 +123,27 @@ class GradientEngine:
             self.channel = comm.new_channel()
             # one contiguous arena range for all buckets => the optimizer can treat it as a single flat tensor
             layouts = []
-            for b in self.buckets:
+            # the last bucket runs after the last gradient with nothing left to hide behind: spread it over many CTAs
+            # (32 KB each instead of 256 KB) so that its pack / reduce phases are short
+            per_cta = [256 << 10] * len(self.buckets)
+            if tail and len(self.buckets) > 1:
+                per_cta[-1] = 32 << 10
+            for b, pc in zip(self.buckets, per_cta):
                 ns = [self.params[i].numel() for i in b.param_ids]
                 offs, total = P.tensor_layout(ns)
-                grid = P.choose_grid(total, esz, min(max_ctas or comm.max_ctas, comm.max_blocks))
+                grid = P.choose_grid(total, esz, min(max_ctas or comm.max_ctas, comm.max_blocks), pc)
                 layouts.append((ns, offs, total, P.build_layout(ns, self.world, grid, offs, total).region_elems))
             self.total_elems = sum(l[3] for l in layouts)
             self.arena_off = comm.alloc(self.total_elems * esz)
             cur = 0
-            for b, (ns, offs, total, region) in zip(self.buckets, layouts):
+            for b, (ns, offs, total, region), pc in zip(self.buckets, layouts, per_cta):
                 b.elem_off, b.region_elems = cur, region
                 b.one_shot = self.world > 1 and region * esz <= ONE_SHOT_MAX_BYTES
                 # one-shot: the pack goes to a private double-buffered staging area, the reduced values land in the
                 # bucket's slot of the gradient arena (result_off_bytes at launch)
                 data_off = comm.alloc(2 * region * esz) if b.one_shot else self.arena_off + cur * esz
                 b.plan = comm.make_plan(ns, wire_dtype, max_ctas=max_ctas, double_buffer=False, offsets=offs, total=total,
-                                        data_off_bytes=data_off)
+                                        data_off_bytes=data_off, bytes_per_cta=pc)
                 assert b.plan.layout.region_elems == region
                 for pid, o in zip(b.param_ids, offs):
                     self.param_elem_off[pid] = cur + o
@@ -197,7 +202,7 @@ class GradientEngine:
                     mview.copy_(old.to(mview.dtype))
                 optimizer.state[p]["momentum_buffer"] = mview
         self._flat = _FlatState(self, master, momentum, model_copy)
-        if not self.bucket_view:
+        if not getattr(self, "bucket_view", False):      # (shared with the single-process DataParallel engine)
             self.writeback = False
         return self._flat
 

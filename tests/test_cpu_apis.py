@@ -37,13 +37,16 @@ hvd.broadcast_optimizer_state(opt, root_rank=0)
 assert opt.param_groups[0]["lr"] == 0.1
 opt = hvd.DistributedOptimizer(opt, named_parameters=m.named_parameters(), compression=hvd.Compression.fp16)
 assert isinstance(opt, torch.optim.SGD)
-for it in range(3):
+for it in range(int(os.environ.get("PTD_TEST_ITERS", "3"))):
     torch.manual_seed(100 + r + it)
     x, y = torch.randn(6, 4), torch.randint(0, 2, (6,))
     opt.zero_grad()
     torch.nn.functional.cross_entropy(m(x), y).backward()
     opt.step()
 eng = opt._ptd_engine_obj
+if os.environ.get("HOROVOD_AUTOTUNE") == "1":
+    assert eng._tuner is not None and eng._tuner.done and eng.cycle_bytes in eng._tuner.cands
+    eng.write_timeline()
 if os.environ.get("PTD_HVD_STATIC") == "1":           # frozen after the first complete step; the hooks launched steps 2 and 3 themselves
     assert eng._schedule is not None and sorted(i for g in eng._schedule for i in g) == list(range(len(eng.params)))
 else:
@@ -78,6 +81,56 @@ def test_hvd_api_over_gloo(tmp_path):
         assert p.stdout.count("HVD-OK") == 2
         sums[static] = sorted(re.findall(r"HVD-SUM \d (-?\d+\.\d+)", p.stdout))      # ranks may interleave their lines
     assert sums["0"] == sums["1"] and len(sums["0"]) == 2
+
+
+def test_hvd_autotune_and_timeline_over_gloo(tmp_path):
+    """HOROVOD_AUTOTUNE=1 sweeps the cycle budget (same winner on every rank), then the static schedule freezes;
+    HOROVOD_TIMELINE writes the fusion-queue trace."""
+    import json
+    script = tmp_path / "hvd_check.py"
+    script.write_text(HVD % ROOT)
+    tl = tmp_path / "timeline.json"
+    env = dict(os.environ, OMP_NUM_THREADS="1", PTD_HVD_STATIC="1", HOROVOD_AUTOTUNE="1", HOROVOD_AUTOTUNE_STEPS_PER_SAMPLE="2",
+               HOROVOD_TIMELINE=str(tl), PTD_TEST_ITERS="24")
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29735", str(script)], env=env, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-3000:]
+    assert p.stdout.count("HVD-OK") == 2 and "[hvd autotune]" in p.stdout
+    tr = json.load(open(tmp_path / "timeline.rank0.json"))
+    assert tr["traceEvents"] and {"name", "ts", "dur", "args"} <= set(tr["traceEvents"][0]) and tr["stats"]["groups"] >= 1
+
+
+def test_fusion_queue_cycle_budget_and_wait_idle():
+    """C++ FusionQueue: groups close at the cycle budget (deterministically), wait_idle blocks without polling, done entries are reaped."""
+    import threading
+    import time
+    from pytorch_distributed_b200 import _ext
+    C = _ext.lib()
+    q = C.FusionQueue(64 << 20, 5.0, 1000)
+    q.enable_timeline(True)
+    hs = [q.enqueue("t%d" % i, 400, i) for i in range(7)]      # 400+400+400 >= 1000 closes a group every 3 tensors
+    g1, g2 = q.next_group(10.0), q.next_group(10.0)
+    assert g1 == hs[0:3] and g2 == hs[3:6] and q.next_group(1.0) == []
+    q.flush()
+    g3 = q.next_group(10.0)
+    assert g3 == hs[6:7] and q.pending() == 7
+    t0 = time.time()
+    assert q.wait_idle(50.0) is False and time.time() - t0 >= 0.04        # still outstanding: times out
+
+    def finish():
+        time.sleep(0.05)
+        q.mark_done(g1 + g2 + g3)
+    th = threading.Thread(target=finish)
+    th.start()
+    assert q.wait_idle(5000.0) is True and q.pending() == 0
+    th.join()
+    tl = q.timeline()
+    assert len(tl) == 7 and tl[0][0] == "t0" and tl[0][2] == 1 and tl[3][2] == 2 and tl[6][2] == 3
+    q.set_cycle_bytes(0)
+    for i in range(5):
+        q.enqueue("u%d" % i, 400, i)
+    assert q.next_group(1.0) == []                              # budget off: only the 64 MiB threshold or a flush closes a group
+    q.shutdown()
 
 
 def test_apex_namespace_surface():

@@ -6,11 +6,11 @@ export PYTHONPATH=$PWD
 O=gpurun_out
 timeout 300 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > $O/a_ref1.json 2> $O/a_ref1.err
 PTD_TIMELINE=$O/a_tl timeout 300 python bench.py --gpus 1 --steps 20 --warmup 5 > $O/a_own1.json 2> $O/a_own1.err
-PTD_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_experimental.py -q -k "not horovod" 2>&1 | tail -40 > $O/a_exp_tests.log
+timeout 600 python -m pytest tests/test_gpu_fused_paths.py -q -k "not horovod" 2>&1 | tail -40 > $O/a_exp_tests.log
 run() { tag=$1; shift; env "$@" timeout 300 python bench.py --gpus 1 --steps 20 --warmup 5 --skip-e2e > $O/a_bench_$tag.json 2> $O/a_bench_$tag.err; }
-run split PTD_SPLIT_RESGRAD=1
-run stem PTD_STEM_GEMM=1
-run both PTD_SPLIT_RESGRAD=1 PTD_STEM_GEMM=1
+run nosplit PTD_SPLIT_RESGRAD=0
+run nostem PTD_STEM_GEMM=0
+run neither PTD_SPLIT_RESGRAD=0 PTD_STEM_GEMM=0
 timeout 200 python tools/stem_gemm_probe.py 256 > $O/a_stem_gemm_probe.md 2>&1
 echo "== ref"; cat $O/a_ref1.json; tail -n 3 $O/a_ref1.err
 echo "== own"; cat $O/a_own1.json; tail -n 3 $O/a_own1.err

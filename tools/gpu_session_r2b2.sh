@@ -4,7 +4,7 @@
 mkdir -p gpurun_out
 export PYTHONPATH=$PWD
 O=gpurun_out
-PTD_TEST_EXPERIMENTAL=1 timeout 1500 python -m pytest tests/test_gpu_multi.py tests/test_gpu_entrypoints.py tests/test_gpu_experimental.py -m gpu -q -k "not bn_backward2 and not im2col" 2>&1 | tail -60 > $O/b2_tests.log
+timeout 1500 python -m pytest tests/test_gpu_multi.py tests/test_gpu_entrypoints.py tests/test_gpu_fused_paths.py tests/test_gpu_single_entry.py -m gpu -q -k "not bn_backward2 and not im2col" 2>&1 | tail -60 > $O/b2_tests.log
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
 P=29700
 run() { tag=$1; shift; P=$((P+1)); env "$@" timeout 300 $TR --master-port $P bench.py --gpus 2 --steps 20 --warmup 5 --skip-e2e $EXTRA > $O/b2_bench_$tag.json 2> $O/b2_bench_$tag.err; }

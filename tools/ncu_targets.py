@@ -140,5 +140,30 @@ def rank():
     dist.destroy_process_group()
 
 
+def stem():
+    """The fused stem at the benchmark shape: im2col + tcgen05 GEMM (+BN statistics) + BN/ReLU/MaxPool forward, and the
+    two-pass quad backward (ncu -k regex:stem_)."""
+    import torch.nn as nn
+    from pytorch_distributed_b200.models.resnet import BNAct
+    from pytorch_distributed_b200.ops.bn_act import begin_step
+    from pytorch_distributed_b200.ops.stem_conv import stem_conv_bn_relu_maxpool
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    conv = nn.Conv2d(3, 64, 7, stride=2, padding=3, bias=False).to(dev).bfloat16().to(memory_format=torch.channels_last)
+    bn = BNAct(64).to(dev).train()
+    x = torch.randn(256, 3, 224, 224, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
+
+    def step():
+        begin_step(dev)
+        y = stem_conv_bn_relu_maxpool(x, conv, bn)
+        y.backward(torch.ones_like(y))
+        conv.weight.grad = None
+        bn.weight.grad = None
+        bn.bias.grad = None
+
+    profiled(step)
+    print("stem done")
+
+
 if __name__ == "__main__":
-    {"single": single, "local": local, "rank": rank}[sys.argv[1]]()
+    {"single": single, "local": local, "rank": rank, "stem": stem}[sys.argv[1]]()
