@@ -236,6 +236,18 @@ def run_own(a):
     metrics.drain()
     ms = max_over_ranks(ev0.elapsed_time(ev1), device)
     value = B * world * K / (ms / 1e3)
+    # PTD_PYPROFILE=<file>: cProfile of 5 extra steps (host-side cost of a step; outside the timed region)
+    if os.environ.get("PTD_PYPROFILE") and rank == 0:
+        import cProfile
+        import pstats
+        pr = cProfile.Profile()
+        pr.enable()
+        for i in range(5):
+            step(*resident[i % len(resident)])
+        pr.disable()
+        torch.cuda.synchronize(device)
+        with open(os.environ["PTD_PYPROFILE"], "w") as f:
+            pstats.Stats(pr, stream=f).sort_stats("cumulative").print_stats(45)
     # PTD_TIMELINE=<prefix>: 3 extra steps under torch.profiler (CUPTI kernel records, also inside graph replays), written as
     # <prefix>.rank<r>.json for tools/timeline_summary.py.  Outside the timed region: the profiler never touches a bench value.
     if os.environ.get("PTD_TIMELINE"):

@@ -96,6 +96,7 @@ class GradientEngine:
         self._overlap_opt = None        # FusedSGD in overlap mode: applies its update per bucket, behind the all-reduce
         self._callback_queued = False
         self._pending_finish = []       # TorchCommunicator async handles
+        self._keepalive = []            # tensors a side-stream kernel still reads (released after the join)
         self._grads_ready_event = None
         self._next_bucket = 0
         esz = P.WIRE_BYTES[wire_dtype]
@@ -273,6 +274,11 @@ class GradientEngine:
                 if opt is not None:
                     opt._apply_slice(b.elem_off, b.region_elems)
             if b.views is not None:
+                if not prepacked:
+                    # the autograd-produced gradients are still being read by the pack pass on the side stream: re-pointing
+                    # p.grad drops their last reference, and the allocator would hand the memory to the next backward kernel
+                    # on the compute stream at once - keep them alive until the end-of-backward join
+                    self._keepalive.append(grads)
                 for pid, v in zip(b.param_ids, b.views):    # torch semantics: after the reduction p.grad IS the bucket view
                     self.params[pid].grad = v
         else:
@@ -293,6 +299,7 @@ class GradientEngine:
             ev.record(self.stream)
             self._grads_ready_event = ev
             torch.cuda.current_stream().wait_event(ev)
+            self._keepalive.clear()
         else:
             for fin in self._pending_finish:
                 fin()

@@ -353,11 +353,19 @@ class DataParallel(nn.Module):
                 saved = [b.detach().clone() for b in m.buffers()]
                 eager = m.forward                      # bound method of the un-graphed module
                 sample = inputs[r].detach().clone()
-                if autocast_state[0]:
-                    with torch.autocast("cuda", dtype=autocast_state[1], cache_enabled=False):
+                # torch.cuda.graph captures on a CLASS-level default stream created on whichever device was current the
+                # first time (device 0): entering it from device r would switch the capture to device 0 while the replica's
+                # kernels run on device r.  Drop it so that this capture creates one on the replica's device.
+                saved_stream = torch.cuda.graph.default_capture_stream
+                torch.cuda.graph.default_capture_stream = None
+                try:
+                    if autocast_state[0]:
+                        with torch.autocast("cuda", dtype=autocast_state[1], cache_enabled=False):
+                            g = torch.cuda.make_graphed_callables(m, (sample,))
+                    else:
                         g = torch.cuda.make_graphed_callables(m, (sample,))
-                else:
-                    g = torch.cuda.make_graphed_callables(m, (sample,))
+                finally:
+                    torch.cuda.graph.default_capture_stream = saved_stream
                 gfwd = g.forward                       # make_graphed_callables patched m.forward: keep both, restore the module
                 m.forward = eager
                 with torch.no_grad():
@@ -402,14 +410,12 @@ class DataParallel(nn.Module):
             self._train_calls += 1
             if self.graph_replicas and self._graphed is None and self._train_calls > self.graph_warmup:
                 self._graph_replicas(inputs, ac)
-        use_graphs = self._graphed is not None and ge and self.module.training
-        if use_graphs:
-            # a graph launch is cheap and asynchronous: no host threads needed
-            outs = [self._replica_forward(r, inputs[r], ge, ac) for r in range(n)]
+        if self._graphed is not None and ge and self.module.training:
             from .. import _ext
             _ext.note_launch(self.graph_launches_per_step)
-        else:
-            futs = [eng.pool.submit(self._replica_forward, r, inputs[r], ge, ac) for r in range(1, n)]
-            outs = [self._replica_forward(0, inputs[0], ge, ac)]
-            outs += [f.result() for f in futs]
+        # replica threads in both modes: launching a ~450-node CUDA graph costs the host ~2 ms and cudaGraphLaunch releases the
+        # GIL, so the per-device launches proceed in parallel (backward: autograd's per-device threads do the same)
+        futs = [eng.pool.submit(self._replica_forward, r, inputs[r], ge, ac) for r in range(1, n)]
+        outs = [self._replica_forward(0, inputs[0], ge, ac)]
+        outs += [f.result() for f in futs]
         return _Gather.apply(eng, *outs)

@@ -175,7 +175,12 @@ def main():
         m.engine.remove_hooks()
         return out, info
 
+    # cuDNN picks non-deterministic wgrad algorithms: two runs of the SAME mode differ; make the runs reproducible and
+    # calibrate the bound with a second default run
+    torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark = True, False
     ref_params, info = run_mode("default", {}, {})
+    again, _ = run_mode("default", {}, {})
+    noise = max((a_ - b_).abs().max().item() / max(1e-2, b_.abs().max().item()) for a_, b_ in zip(again, ref_params))
     modes = [("bucket_view+arena memset", dict(gradient_as_bucket_view=True), {}, "arena"),
              ("bucket_view+set_to_none", dict(gradient_as_bucket_view=True), {}, "none"),
              ("small buckets (one-shot)", dict(bucket_cap_mb=0.2, tail_bucket_mb=0.05), {}, "none"),
@@ -188,13 +193,14 @@ def main():
             assert world == 1 or inf[1] >= 3, "expected one-shot buckets, got %r" % (inf,)
         for i, (a_, b_) in enumerate(zip(got, ref_params)):
             err = (a_ - b_).abs().max().item()
-            lim = 2e-4 * max(1e-2, b_.abs().max().item())
+            lim = max(2e-4, 20 * noise) * max(1e-2, b_.abs().max().item())
             assert err <= lim, "engine mode %r: parameter %d differs from the default engine by %g > %g" % (tag, i, err, lim)
         lo, hi = torch.cat([t.reshape(-1) for t in got]), torch.cat([t.reshape(-1) for t in got])
         lo, hi = lo.clone(), hi.clone()
         dist.all_reduce(lo, op=dist.ReduceOp.MIN)
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         assert torch.equal(lo, hi), "engine mode %r: ranks diverged" % tag
+    torch.backends.cudnn.deterministic = False
     # running statistics follow rank 0 after a training forward (deferred broadcast) on every rank
     torch.manual_seed(3)
     mb = DistributedDataParallel(create_model("resnet18", num_classes=10, fused_bn=False).to(dev), device_ids=[local], comm=comm, wire_dtype="fp32")
