@@ -292,18 +292,43 @@ __global__ void __launch_bounds__(kThreads) oneshot_allreduce_kernel(const __gri
   const int64_t blk_bytes = (int64_t)blockIdx.x * a.block_elems * sizeof(W);
   const int units = (int)(a.block_elems / kUnitElems);
   bool bad = false;
-  for (int u = threadIdx.x; u < units; u += kThreads) {
-    const int64_t off = stage_off + blk_bytes + (int64_t)u * 16;
-    V4 v;
-    if constexpr (NVLS) {
-      v = Multimem<W>::ld_reduce(c.mc_base + off);
-    } else {
-      float acc[sizeof(W) == 4 ? 4 : 8];
-      p2p_reduce_unit<W>(c, off, acc);
-      v = to_unit<W>(acc);
+  {
+    // latency-bound by design (one traversal of the switch per unit): keep 8 requests in flight per thread
+    constexpr int U = 8;
+    const int64_t src0 = stage_off + blk_bytes, dst0 = result_off + blk_bytes;
+    int u = threadIdx.x;
+    for (; u + (U - 1) * kThreads < units; u += U * kThreads) {
+      V4 v[U];
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        const int64_t off = src0 + (int64_t)(u + k * kThreads) * 16;
+        if constexpr (NVLS) {
+          v[k] = Multimem<W>::ld_reduce(c.mc_base + off);
+        } else {
+          float acc[sizeof(W) == 4 ? 4 : 8];
+          p2p_reduce_unit<W>(c, off, acc);
+          v[k] = to_unit<W>(acc);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        if (a.found_inf) bad |= unit_nonfinite<W>(v[k]);
+        st_v4(c.base[c.rank] + dst0 + (int64_t)(u + k * kThreads) * 16, v[k]);
+      }
     }
-    if (a.found_inf) bad |= unit_nonfinite<W>(v);
-    st_v4(c.base[c.rank] + result_off + blk_bytes + (int64_t)u * 16, v);
+    for (; u < units; u += kThreads) {
+      const int64_t off = src0 + (int64_t)u * 16;
+      V4 v;
+      if constexpr (NVLS) {
+        v = Multimem<W>::ld_reduce(c.mc_base + off);
+      } else {
+        float acc[sizeof(W) == 4 ? 4 : 8];
+        p2p_reduce_unit<W>(c, off, acc);
+        v = to_unit<W>(acc);
+      }
+      if (a.found_inf) bad |= unit_nonfinite<W>(v);
+      st_v4(c.base[c.rank] + dst0 + (int64_t)u * 16, v);
+    }
   }
   if (a.found_inf && __syncthreads_or(bad) && threadIdx.x == 0) {
     // every rank reduced the same values, so every rank takes the same decision: a local store is enough
@@ -313,6 +338,37 @@ __global__ void __launch_bounds__(kThreads) oneshot_allreduce_kernel(const __gri
   if (a.writeback) unpack_block<W>(pk, a, reinterpret_cast<const W*>(c.base[c.rank] + result_off), false);
   if (threadIdx.x == 0) a.plan_calls[blockIdx.x] = call + 1;
   store_seq(c, seq);
+}
+
+// Replicate `units` 16-byte units starting at arena byte offset `off0` from the local arena into every peer's
+// (one multimem.st per unit through the switch, or W-1 peer stores): 4 loads in flight per thread.
+template <bool NVLS>
+__device__ __forceinline__ void push_range(const CommCtx& c, int64_t off0, int units) {
+  constexpr int U = 4;
+  int u = threadIdx.x;
+  for (; u + (U - 1) * kThreads < units; u += U * kThreads) {
+    V4 v[U];
+#pragma unroll
+    for (int k = 0; k < U; ++k) v[k] = ld_sys(c.base[c.rank] + off0 + (int64_t)(u + k * kThreads) * 16);
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const int64_t off = off0 + (int64_t)(u + k * kThreads) * 16;
+      if constexpr (NVLS) {
+        multimem_st(c.mc_base + off, v[k]);
+      } else {
+        for (int i = 1; i < c.world; ++i) st_sys(c.base[(c.rank + i) % c.world] + off, v[k]);
+      }
+    }
+  }
+  for (; u < units; u += kThreads) {
+    const int64_t off = off0 + (int64_t)u * 16;
+    V4 v = ld_sys(c.base[c.rank] + off);
+    if constexpr (NVLS) {
+      multimem_st(c.mc_base + off, v);
+    } else {
+      for (int i = 1; i < c.world; ++i) st_sys(c.base[(c.rank + i) % c.world] + off, v);
+    }
+  }
 }
 
 // ================================================================= K2: fused multi-tensor broadcast
@@ -333,15 +389,7 @@ __global__ void __launch_bounds__(kThreads) fused_broadcast_kernel(const __grid_
     // push my CTA range to everyone else
     const int64_t off0 = data_off + (int64_t)blockIdx.x * a.block_elems * sizeof(W);
     const int units = (int)(a.block_elems / kUnitElems);
-    for (int u = threadIdx.x; u < units; u += kThreads) {
-      const int64_t off = off0 + (int64_t)u * 16;
-      V4 v = ld_sys(c.base[c.rank] + off);
-      if constexpr (NVLS) {
-        multimem_st(c.mc_base + off, v);
-      } else {
-        for (int i = 1; i < c.world; ++i) st_sys(c.base[(c.rank + i) % c.world] + off, v);
-      }
-    }
+    push_range<NVLS>(c, off0, units);
   }
   block_barrier(c, seq);
   if (c.rank != a.root) unpack_block<W>(pk, a, local, false);
@@ -375,17 +423,37 @@ __global__ void __launch_bounds__(kThreads) reduce_to_caller_kernel(const __grid
   constexpr int kUnitElems = 16 / sizeof(W);
   const int64_t off0 = a.data_off_bytes + (int64_t)blockIdx.x * a.block_elems * sizeof(W);
   const int units = (int)(a.block_elems / kUnitElems);
-  for (int u = threadIdx.x; u < units; u += kThreads) {
-    const int64_t off = off0 + (int64_t)u * 16;
-    V4 v;
-    if constexpr (NVLS) {
-      v = Multimem<W>::ld_reduce(c.mc_base + off);
-    } else {
-      float acc[sizeof(W) == 4 ? 4 : 8];
-      p2p_reduce_unit<W>(c, off, acc);
-      v = to_unit<W>(acc);
+  {
+    constexpr int U = 8;       // the root pulls every unit through the switch: 8 in-switch reductions in flight per thread
+    int u = threadIdx.x;
+    for (; u + (U - 1) * kThreads < units; u += U * kThreads) {
+      V4 v[U];
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        const int64_t off = off0 + (int64_t)(u + k * kThreads) * 16;
+        if constexpr (NVLS) {
+          v[k] = Multimem<W>::ld_reduce(c.mc_base + off);
+        } else {
+          float acc[sizeof(W) == 4 ? 4 : 8];
+          p2p_reduce_unit<W>(c, off, acc);
+          v[k] = to_unit<W>(acc);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < U; ++k) st_v4(c.base[c.rank] + off0 + (int64_t)(u + k * kThreads) * 16, v[k]);
     }
-    st_v4(c.base[c.rank] + off, v);
+    for (; u < units; u += kThreads) {
+      const int64_t off = off0 + (int64_t)u * 16;
+      V4 v;
+      if constexpr (NVLS) {
+        v = Multimem<W>::ld_reduce(c.mc_base + off);
+      } else {
+        float acc[sizeof(W) == 4 ? 4 : 8];
+        p2p_reduce_unit<W>(c, off, acc);
+        v = to_unit<W>(acc);
+      }
+      st_v4(c.base[c.rank] + off, v);
+    }
   }
   if (a.writeback) {
     __syncthreads();
@@ -401,15 +469,7 @@ __global__ void __launch_bounds__(kThreads) push_kernel(const __grid_constant__ 
   __syncthreads();
   const int64_t off0 = a.data_off_bytes + (int64_t)blockIdx.x * a.block_elems * sizeof(W);
   const int units = (int)(a.block_elems / kUnitElems);
-  for (int u = threadIdx.x; u < units; u += kThreads) {
-    const int64_t off = off0 + (int64_t)u * 16;
-    V4 v = ld_sys(c.base[c.rank] + off);
-    if constexpr (NVLS) {
-      multimem_st(c.mc_base + off, v);
-    } else {
-      for (int i = 1; i < c.world; ++i) st_sys(c.base[(c.rank + i) % c.world] + off, v);
-    }
-  }
+  push_range<NVLS>(c, off0, units);
 }
 
 // ================================================================= K3: barrier
@@ -565,7 +625,8 @@ static void launch_kind(int kind, int grid, cudaStream_t st, const CommCtx& c, c
 void launch_plan(const CommCtx& ctx, int kind, int wire_dtype, bool nvls, int grid, const std::vector<at::Tensor>& tensors,
                  int64_t seg_begin_ptr, int64_t segs_ptr, int64_t data_off_bytes, int64_t block_elems, int64_t plan_calls_ptr,
                  int64_t found_inf_ptr, double scale, bool writeback, int root, int flags, int64_t result_off_bytes) {
-  TORCH_CHECK(grid >= 1 && grid <= kMaxBlocks, "grid out of range");
+  // kinds 0-2 synchronise through the per-CTA flag table (kMaxBlocks rows); the host-synchronised kinds 3-6 carry no flags
+  TORCH_CHECK(grid >= 1 && (grid <= kMaxBlocks || kind >= 3), "grid out of range");
   TORCH_CHECK(!nvls || ctx.mc_base != nullptr, "NVLS variant requested but no multicast mapping");
   PtrPack pk;
   fill_ptrs(pk, tensors);

@@ -411,7 +411,7 @@ class HorovodStrategy(Strategy):
     """/root/reference/horovod_distributed.py: broadcast_parameters + DistributedOptimizer(compression=fp16)."""
     name = "horovod_distributed"
     overlap_optimizer = False   # horovod semantics: step() synchronises the handles first, then updates
-    cast_params = False         # gradients come back decompressed to fp32 into p.grad: keep fp32 weights + autocast
+    cast_params = True          # bf16 model (tcgen05 conv / stem GEMM paths need bf16 weights); fp32 masters live in FusedSGD
     # the fusion dispatcher is a host thread: not capturable - unless the static schedule replaces it after the first step
     graph_capable = os.environ.get("PTD_HVD_STATIC", "1") == "1" and os.environ.get("HOROVOD_AUTOTUNE", "0") != "1"
 
@@ -430,6 +430,10 @@ class HorovodStrategy(Strategy):
         hvd = self.hvd
         model = self.prepare_model(model, args, device)
         hvd.broadcast_parameters(model.state_dict(), root_rank=0)
+        # the fp32 values stashed by the bf16 cast become the optimizer's master weights: they must be rank 0's too
+        inits = [p._ptd_master_init for p in model.parameters() if getattr(p, "_ptd_master_init", None) is not None]
+        if inits and hvd.size() > 1:
+            hvd.communicator().broadcast_(inits, root=0)
         optimizer = self.make_optimizer(model, args)
         hvd.broadcast_optimizer_state(optimizer, root_rank=0)
         comp = {"none": hvd.Compression.none, "fp16": hvd.Compression.fp16, "bf16": hvd.Compression.bf16}[args.compression]
@@ -535,7 +539,7 @@ def main_worker(local_rank: int, nprocs: int, args, strategy: Optional[Strategy]
             save_checkpoint({
                 "epoch": epoch + 1,
                 "arch": args.arch,
-                "state_dict": export_state_dict(st.unwrapped(model), getattr(st, "engine", None)),
+                "state_dict": export_state_dict(st.unwrapped(model), getattr(st, "engine", None), optimizer),
                 "best_acc1": best_acc1,
                 "optimizer": optimizer.state_dict() if args.resume or os.environ.get("PTD_SAVE_OPTIMIZER") else None,
                 "amp": st.amp.state_dict() if hasattr(st, "amp") else None,      # loss-scaler state (apex entrypoint)

@@ -175,21 +175,36 @@ class FusedSGD(Optimizer):
                 st["momentum_buffer"] = torch.zeros_like(p, dtype=torch.float32, memory_format=torch.preserve_format)
                 st["_fresh"] = True
             bufs.append(st["momentum_buffer"])
-        if params[0].is_cuda and all(p.dtype == torch.float32 for p in params):
+        if params[0].is_cuda and all(p.dtype in (torch.float32, torch.bfloat16, torch.float16) for p in params):
             from .. import _ext
             C = _ext.lib()
             hyper = self._hyper_tensor(gi, group, params[0].device)
             if amp is not None:
                 amp.attach_hyper(hyper)
             fresh = [p for p in params if self.state[p].pop("_fresh", False)]
-            if fresh and len(fresh) != len(params):
-                # rare: parameters that got their first gradient later than the others
-                for sub, f in ((fresh, True), ([p for p in params if p not in set(fresh)], False)):
-                    C.fused_sgd_multi([p.grad for p in sub], list(sub), [self.state[p]["momentum_buffer"] for p in sub], [], hyper,
-                                      amp.found_inf if amp is not None else None, bool(group["nesterov"]), f)
-            else:
-                C.fused_sgd_multi([p.grad for p in params], params, bufs, [], hyper,
-                                  amp.found_inf if amp is not None else None, bool(group["nesterov"]), bool(fresh))
+
+            def master_of(p):
+                """fp32 tensor the kernel updates for a low-precision parameter (multi-tensor mode of a bf16 / fp16 model without
+                a flat engine, e.g. under hvd.DistributedOptimizer); the parameter itself is refreshed from it as the model copy."""
+                st = self.state[p]
+                if "master" not in st:
+                    init = getattr(p, "_ptd_master_init", None)         # fp32 values stashed by amp.cast_model
+                    st["master"] = (init if init is not None else p.detach().float()).clone(memory_format=torch.preserve_format)
+                    if init is not None:
+                        del p._ptd_master_init
+                return st["master"]
+
+            fs = set(fresh) if (fresh and len(fresh) != len(params)) else None      # rare: first gradient later than the others
+            for first_flag, sub in ((True, fresh), (False, [p for p in params if p not in fs])) if fs is not None else ((bool(fresh), params),):
+                full = [p for p in sub if p.dtype == torch.float32]
+                low = [p for p in sub if p.dtype != torch.float32]
+                if full:
+                    C.fused_sgd_multi([p.grad for p in full], full, [self.state[p]["momentum_buffer"] for p in full], [], hyper,
+                                      amp.found_inf if amp is not None else None, bool(group["nesterov"]), first_flag)
+                if low:
+                    C.fused_sgd_multi([p.grad for p in low], [master_of(p) for p in low], [self.state[p]["momentum_buffer"] for p in low],
+                                      [p.data for p in low], hyper, amp.found_inf if amp is not None else None, bool(group["nesterov"]),
+                                      first_flag)
         else:
             if amp is not None and amp.host_found_inf():
                 return

@@ -232,6 +232,12 @@ class FusedCommunicator:
 
     def make_plan(self, numels: Sequence[int], wire: str = "bf16", max_ctas: Optional[int] = None, double_buffer: bool = False,
                   **kw) -> Plan:
+        if "bytes_per_cta" not in kw:
+            nbytes = sum(int(n) for n in numels) * P.WIRE_BYTES[wire]
+            if double_buffer and nbytes <= (4 << 20):
+                # latency-bound payloads (one-shot all-reduce, small broadcasts such as the BN buffers' 106 tiny tensors):
+                # many small CTA ranges => short per-CTA segment loops and more requests in flight
+                kw["bytes_per_cta"] = 16 << 10
         return Plan(self, numels, wire, max_ctas or self.max_ctas, double_buffer, **kw)
 
     def check(self) -> None:

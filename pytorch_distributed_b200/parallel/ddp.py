@@ -129,9 +129,13 @@ class GradientEngine:
             per_cta = [256 << 10] * len(self.buckets)
             if tail and len(self.buckets) > 1:
                 per_cta[-1] = 32 << 10
-            for b, pc in zip(self.buckets, per_cta):
+            for k, b in enumerate(self.buckets):
                 ns = [self.params[i].numel() for i in b.param_ids]
                 offs, total = P.tensor_layout(ns)
+                b.one_shot = self.world > 1 and total * esz <= ONE_SHOT_MAX_BYTES
+                if b.one_shot:
+                    per_cta[k] = 16 << 10      # latency-bound: many small CTA ranges, all requests in flight at once
+                pc = per_cta[k]
                 grid = P.choose_grid(total, esz, min(max_ctas or comm.max_ctas, comm.max_blocks), pc)
                 layouts.append((ns, offs, total, P.build_layout(ns, self.world, grid, offs, total).region_elems))
             self.total_elems = sum(l[3] for l in layouts)
@@ -139,7 +143,6 @@ class GradientEngine:
             cur = 0
             for b, (ns, offs, total, region), pc in zip(self.buckets, layouts, per_cta):
                 b.elem_off, b.region_elems = cur, region
-                b.one_shot = self.world > 1 and region * esz <= ONE_SHOT_MAX_BYTES
                 # one-shot: the pack goes to a private double-buffered staging area, the reduced values land in the
                 # bucket's slot of the gradient arena (result_off_bytes at launch)
                 data_off = comm.alloc(2 * region * esz) if b.one_shot else self.arena_off + cur * esz

@@ -51,8 +51,11 @@ class LocalCommunicator:
         self.world = len(devices)
         self.rank = 0
         self.device = torch.device("cuda", devices[0])
-        self.max_blocks = self._C.MAX_BLOCKS
-        self.max_ctas = 32
+        # the single-process kernels (pack / push / reduce-to-caller / unpack) carry no cross-GPU flags, so they are not bound by
+        # the flag table (MAX_BLOCKS): two CTAs per SM keep enough multimem requests in flight to approach the link rate
+        sms = torch.cuda.get_device_properties(devices[0]).multi_processor_count
+        self.max_blocks = 2 * sms
+        self.max_ctas = 2 * sms
         self.arena = self._C.SymmArena.create_local(self.devices, arena_bytes, allow_nvls)
         self.nvls = bool(self.arena.has_multicast)
         self.header_bytes = P.round_up(self._C.SIGNAL_PAD_BYTES, 128 << 10)
@@ -94,7 +97,7 @@ class _TensorSet:
         for g in groups:
             ns = [numels[i] for i in g]
             offs, total = P.tensor_layout(ns)
-            grid = P.choose_grid(total, esz, comm.max_ctas)
+            grid = P.choose_grid(total, esz, comm.max_ctas, 128 << 10)
             layouts.append((ns, offs, total, grid, P.build_layout(ns, comm.world, grid, offs, total).region_elems))
         self.total_elems = sum(l[4] for l in layouts)
         self.arena_off = comm.alloc(max(self.total_elems, 8) * esz)
@@ -102,8 +105,8 @@ class _TensorSet:
         self.plans = []     # plans[group][device_slot]
         cur = 0
         for g, (ns, offs, total, grid, region) in zip(groups, layouts):
-            row = [Plan(comm, ns, wire, grid, False, offsets=offs, total=total, data_off_bytes=self.arena_off + cur * esz, rank_slot=r)
-                   for r in range(comm.world)]
+            row = [Plan(comm, ns, wire, grid, False, offsets=offs, total=total, data_off_bytes=self.arena_off + cur * esz, rank_slot=r,
+                        bytes_per_cta=128 << 10) for r in range(comm.world)]
             self.plans.append(row)
             for i, o in zip(g, offs):
                 self.elem_off[i] = cur + o

@@ -308,7 +308,10 @@ class _FusionEngine:
                 p.grad = g
             grads.append(g)
         if self.fused:
-            wire = self.wire or ("fp32" if grads[0].dtype == torch.float32 else ("bf16" if grads[0].dtype == torch.bfloat16 else "fp16"))
+            own = "fp32" if grads[0].dtype == torch.float32 else ("bf16" if grads[0].dtype == torch.bfloat16 else "fp16")
+            # "compression" = the wire dtype of the fused kernel; gradients that already are 16-bit travel as they are
+            # (casting bf16 to fp16 would only lose range)
+            wire = own if own != "fp32" else (self.wire or own)
             if ready_event is not None:
                 self.stream.wait_event(ready_event)
             for lo in range(0, len(ids), 256):      # one kernel launch carries at most 256 tensor pointers

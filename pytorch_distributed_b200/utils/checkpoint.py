@@ -14,10 +14,16 @@ import shutil
 import torch
 
 
-def export_state_dict(module: torch.nn.Module, engine=None):
-    """fp32 ``state_dict`` of the unwrapped module; master weights replace low-precision model copies."""
+def export_state_dict(module: torch.nn.Module, engine=None, optimizer=None):
+    """fp32 ``state_dict`` of the unwrapped module; master weights replace low-precision model copies (flat engines keep them
+    in the engine, the multi-tensor optimizer path in ``optimizer.state[p]["master"]``)."""
     sd = module.state_dict()
     masters = {}
+    if optimizer is not None:
+        for name, p in module.named_parameters():
+            m = optimizer.state.get(p, {}).get("master") if hasattr(optimizer, "state") else None
+            if m is not None:
+                masters[name] = m
     if engine is not None and hasattr(engine, "master_params"):
         idx = {id(p): i for i, p in enumerate(engine.params)}
         mp = engine.master_params()

@@ -18,3 +18,8 @@ RANK=0 LOCAL_RANK=0 timeout 600 $NCU -k regex:"fused_allreduce|fused_broadcast" 
 wait $R1
 ls -la $O/*.ncu-rep
 tail -n 3 $O/ncu_single.log $O/ncu_stem.log $O/ncu_local.log $O/ncu_rank0.log $O/ncu_rank1.log
+# re-measure the latency-bound collectives after the unroll / granularity changes
+P=29950; timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port $P tools/comm_bench.py k1small k2 > $O/ncu_comm_bench2.md 2> $O/ncu_comm_bench2.err
+timeout 200 python tools/comm_bench.py local > $O/ncu_comm_local2.md 2> $O/ncu_comm_local2.err
+cat $O/ncu_comm_bench2.md $O/ncu_comm_local2.md; tail -2 $O/ncu_comm_bench2.err $O/ncu_comm_local2.err
+timeout 600 python -m pytest tests/test_gpu_multi.py -q 2>&1 | tail -5
