@@ -89,6 +89,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         launch_ll_allreduce(a->ctx(channel), in, out, scale, a->ll_seq_ptr());
       });
 
+  m.def("pack_pointers", &pack_pointers);
   m.def("fused_sgd_flat", &fused_sgd_flat, py::arg("grad"), py::arg("master"), py::arg("momentum"), py::arg("model_copy"), py::arg("hyper"),
         py::arg("found_inf"), py::arg("nesterov"), py::arg("first_step"));
   m.def("fused_sgd_multi", &fused_sgd_multi);

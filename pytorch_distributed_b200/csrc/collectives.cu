@@ -607,6 +607,17 @@ static void fill_ptrs(PtrPack& pk, const std::vector<at::Tensor>& ts) {
   }
 }
 
+// The pointer pack of a tensor list as an opaque CPU byte tensor: build it once for lists whose storage never moves
+// (parameters of persistent replicas, static gradient buffers of captured graphs) and pass [pack] instead of the list.
+at::Tensor pack_pointers(const std::vector<at::Tensor>& tensors) {
+  at::Tensor out = at::zeros({(int64_t)sizeof(PtrPack)}, at::TensorOptions().dtype(at::kByte));
+  PtrPack pk;
+  memset(&pk, 0, sizeof(pk));
+  fill_ptrs(pk, tensors);
+  memcpy(out.data_ptr(), &pk, sizeof(PtrPack));
+  return out;
+}
+
 template <typename W, bool NVLS>
 static void launch_kind(int kind, int grid, cudaStream_t st, const CommCtx& c, const PtrPack& pk, const PlanArgs& a) {
   switch (kind) {
@@ -629,7 +640,12 @@ void launch_plan(const CommCtx& ctx, int kind, int wire_dtype, bool nvls, int gr
   TORCH_CHECK(grid >= 1 && (grid <= kMaxBlocks || kind >= 3), "grid out of range");
   TORCH_CHECK(!nvls || ctx.mc_base != nullptr, "NVLS variant requested but no multicast mapping");
   PtrPack pk;
-  fill_ptrs(pk, tensors);
+  if (tensors.size() == 1 && tensors[0].is_cpu() && tensors[0].scalar_type() == at::kByte && tensors[0].numel() == (int64_t)sizeof(PtrPack)) {
+    // pre-built pointer pack (pack_pointers()): persistent tensor lists skip the per-launch list conversion and checks
+    memcpy(&pk, tensors[0].data_ptr(), sizeof(PtrPack));
+  } else {
+    fill_ptrs(pk, tensors);
+  }
   PlanArgs a;
   a.seg_begin = reinterpret_cast<const int32_t*>(seg_begin_ptr);
   a.segs = reinterpret_cast<const Seg*>(segs_ptr);

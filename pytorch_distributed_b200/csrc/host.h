@@ -23,6 +23,7 @@ static_assert(sizeof(Seg) == 24, "Seg layout is mirrored by numpy in parallel/pl
 void launch_plan(const CommCtx& ctx, int kind, int wire_dtype, bool nvls, int grid, const std::vector<at::Tensor>& tensors,
                  int64_t seg_begin_ptr, int64_t segs_ptr, int64_t data_off_bytes, int64_t block_elems, int64_t plan_calls_ptr,
                  int64_t found_inf_ptr, double scale, bool writeback, int root, int flags = 0, int64_t result_off_bytes = -1);
+at::Tensor pack_pointers(const std::vector<at::Tensor>& tensors);
 void launch_barrier(const CommCtx& ctx);
 void launch_metrics(const CommCtx& ctx, const at::Tensor& logits, const at::Tensor& target, const c10::optional<at::Tensor>& loss,
                     int64_t ll_seq_ptr, at::Tensor out);

@@ -75,6 +75,7 @@ class LocalCommunicator:
         pass
 
     def run(self, plan: Plan, tensors, kind: int, rank_slot: int, scale: float = 1.0, writeback: bool = True) -> None:
+        """``tensors``: a list of tensors, or ``[pack]`` with a pointer pack from ``_C.pack_pointers`` (persistent lists)."""
         with torch.cuda.device(self.devices[rank_slot]):
             self._ext.note_launch()
             self.arena.launch_plan(0, rank_slot, kind, P.WIRE_CODES[plan.wire], self.nvls, plan.grid, tensors,
@@ -112,10 +113,20 @@ class _TensorSet:
                 self.elem_off[i] = cur + o
             cur += region
 
-    def launch(self, kind: int, slot: int, scale: float = 1.0, writeback: bool = True, tensors=None):
+    def launch(self, kind: int, slot: int, scale: float = 1.0, writeback: bool = True, tensors=None, packs=None):
+        """``packs``: per-group pointer packs from :meth:`make_packs` (skips the per-launch tensor-list marshalling)."""
+        if packs is not None:
+            for row, pk in zip(self.plans, packs):
+                self.comm.run(row[slot], [pk], kind, slot, scale=scale, writeback=writeback)
+            return
         ts = self.per_device[slot] if tensors is None else tensors
         for g, row in zip(self.groups, self.plans):
             self.comm.run(row[slot], [ts[i] for i in g], kind, slot, scale=scale, writeback=writeback)
+
+    def make_packs(self, tensors):
+        """Pointer packs (one per group) of a tensor list whose storage does not move."""
+        C = self.comm._C
+        return [C.pack_pointers([tensors[i] for i in g]) for g in self.groups]
 
     def flat(self, slot: int = 0) -> torch.Tensor:
         return self.comm.arena.view(self.arena_off, self.total_elems, _VIEW_NAME[self.wire], slot)
@@ -157,6 +168,71 @@ class _Gather(torch.autograd.Function):
             grads.append(g if dev == grad.device else g.to(dev, non_blocking=True))
             off += n
         return (None,) + tuple(grads)
+
+
+class _ReplicaGraph:
+    """Forward and backward of ONE replica as two CUDA graphs on its device, with static input / output / gradient buffers.
+
+    Unlike ``torch.cuda.make_graphed_callables`` the parameter gradients never re-enter autograd: the backward graph leaves
+    them in ``static_grads`` (fixed addresses), which the K5 pack reads directly - no per-parameter AccumulateGrad, no
+    per-parameter Python at all in the steady state (8 replicas x 161 parameters of ResNet-50 cost the host ~9 ms per step
+    that way, profiles/r2_logs/dp8_host_profile_before.txt).
+    """
+
+    def __init__(self, module, params, sample, device, autocast_state):
+        import contextlib
+        self.device = device
+        self.fresh = False
+        with torch.cuda.device(device):
+            def ctx():
+                return (torch.autocast("cuda", dtype=autocast_state[1], cache_enabled=False) if autocast_state[0]
+                        else contextlib.nullcontext())
+            saved = [b.detach().clone() for b in module.buffers()]     # warm-up + capture run BatchNorm updates: undone below
+            self.static_x = sample.detach().clone()
+            self.token = torch.zeros((), device=self.static_x.device, requires_grad=True)   # ties the output into autograd
+            stream = torch.cuda.Stream(device=device)                  # capture stream on THIS device
+            stream.wait_stream(torch.cuda.current_stream(device))
+            with torch.cuda.stream(stream):
+                for _ in range(3):                                     # cuDNN autotuning, lazy workspaces
+                    with ctx():
+                        out = module(self.static_x)
+                    g = torch.autograd.grad(out, params, torch.zeros_like(out), allow_unused=True)
+                    del out, g
+            stream.synchronize()
+            pool = torch.cuda.graph_pool_handle()
+            self.g_fwd = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.g_fwd, pool=pool, stream=stream):
+                with ctx():
+                    self.static_out = module(self.static_x)
+            self.static_gout = torch.zeros_like(self.static_out)
+            self.g_bwd = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.g_bwd, pool=pool, stream=stream):
+                grads = torch.autograd.grad(self.static_out, params, self.static_gout, allow_unused=True)
+            self.static_grads = [g if g is not None else torch.zeros_like(p) for g, p in zip(grads, params)]
+            torch.cuda.current_stream(device).wait_stream(stream)
+            with torch.no_grad():
+                for b, old in zip(module.buffers(), saved):
+                    b.copy_(old)
+            self.shape, self.dtype = self.static_x.shape, self.static_x.dtype
+
+
+class _Replay(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rep, x, token):
+        ctx.rep = rep
+        with torch.cuda.device(rep.device):
+            rep.static_x.copy_(x)
+            rep.g_fwd.replay()
+        return rep.static_out.detach()
+
+    @staticmethod
+    def backward(ctx, gout):
+        rep = ctx.rep
+        with torch.cuda.device(rep.device):
+            rep.static_gout.copy_(gout)
+            rep.g_bwd.replay()
+        rep.fresh = True               # static_grads now hold this step's gradients of the replica
+        return None, None, None
 
 
 class _ArmReduce(torch.autograd.Function):
@@ -204,6 +280,9 @@ class DataParallelEngine:
         self._flat: Optional[_FlatState] = None
         self._armed = False
         self._grads_ready_event = None
+        self.graphs = None              # per replica _ReplicaGraph (DataParallel(graph_replicas=True))
+        self._grad_packs = None         # pointer packs of the replicas' static gradient buffers
+        self._value_cache = {}          # module index -> (first data_ptr, tensor list, pointer packs)
         self.pool = ThreadPoolExecutor(max_workers=max(1, self.world - 1), thread_name_prefix="ptd-dp")
         ref = weakref.ref(self)
         for pid, p in enumerate(self.params):
@@ -223,8 +302,20 @@ class DataParallelEngine:
 
     @staticmethod
     def _values(m):
-        # evaluated at every launch: a flat optimizer may have re-pointed ``p.data`` since construction
         return [p.data for p in m.parameters()] + [b for b in m.buffers() if b.is_floating_point()]
+
+    def _value_packs(self, r):
+        """Pointer packs of replica ``r``'s parameters + float buffers.  Walking the module tree and marshalling 267 tensors
+        per replica per step is host time a single process does not have; the lists only change when a flat optimizer
+        re-points ``p.data`` (detected through the first parameter's address)."""
+        m = self.modules[r]
+        first = next(m.parameters()).data_ptr()
+        ent = self._value_cache.get(r)
+        if ent is None or ent[0] != first:
+            vals = self._values(m)
+            ent = (first, vals, self.bcast.make_packs(vals))
+            self._value_cache[r] = ent
+        return ent[2]
 
     # ---- K2': root -> all replicas
     def broadcast_values(self):
@@ -237,13 +328,13 @@ class DataParallelEngine:
             with torch.cuda.device(self.devices[r]):
                 ev.record(torch.cuda.current_stream())
             root_stream.wait_event(ev)
-        self.bcast.launch(KIND_PUSH, 0, tensors=self._values(self.modules[0]))
+        self.bcast.launch(KIND_PUSH, 0, packs=self._value_packs(0))
         ev = torch.cuda.Event()
         ev.record(root_stream)
         for r in range(1, self.world):
             with torch.cuda.device(self.devices[r]):
                 torch.cuda.current_stream().wait_event(ev)
-                self.bcast.launch(KIND_UNPACK, r, tensors=self._values(self.modules[r]))
+                self.bcast.launch(KIND_UNPACK, r, packs=self._value_packs(r))
 
     # ---- K5: all replicas -> root
     def _arm_reduce(self):
@@ -254,23 +345,34 @@ class DataParallelEngine:
     def _reduce(self):
         self._armed = False
         root_stream = torch.cuda.current_stream(self.root_device)
+        graphed = self.graphs is not None and all(g.fresh for g in self.graphs)
         for r in range(self.world):
             ps = self.rparams[r]
             with torch.cuda.device(self.devices[r]):
-                grads = []
-                for p in ps:
-                    if p.grad is None:
-                        p.grad = torch.zeros_like(p, memory_format=torch.preserve_format)
-                    grads.append(p.grad if is_dense(p.grad) else p.grad.contiguous())
-                self.grads.launch(KIND_PACK, r, scale=1.0, tensors=grads)
+                if graphed:             # the backward graph left the gradients in static buffers: prebuilt pointer pack
+                    self.graphs[r].fresh = False
+                    self.grads.launch(KIND_PACK, r, scale=1.0, packs=self._grad_packs[r])
+                else:
+                    grads = []
+                    for p in ps:
+                        if p.grad is None:
+                            p.grad = torch.zeros_like(p, memory_format=torch.preserve_format)
+                        grads.append(p.grad if is_dense(p.grad) else p.grad.contiguous())
+                    self.grads.launch(KIND_PACK, r, scale=1.0, tensors=grads)
                 if r > 0:
                     ev = torch.cuda.Event()
                     ev.record(torch.cuda.current_stream())
                     root_stream.wait_event(ev)
         with torch.cuda.device(self.root_device):
-            root_grads = [p.grad for p in self.rparams[0]]
+            if graphed and self.writeback:
+                for p, g in zip(self.rparams[0], self.graphs[0].static_grads):     # the reduced values are unpacked into these
+                    p.grad = g
+            root_grads = self.graphs[0].static_grads if graphed else [p.grad for p in self.rparams[0]]
             if self.world > 1:          # world == 1: the pack above already left this device's gradients in the arena
-                self.grads.launch(KIND_REDUCE, 0, writeback=self.writeback, tensors=root_grads)
+                if graphed:
+                    self.grads.launch(KIND_REDUCE, 0, writeback=self.writeback, packs=self._grad_packs[0])
+                else:
+                    self.grads.launch(KIND_REDUCE, 0, writeback=self.writeback, tensors=root_grads)
             ev = torch.cuda.Event()
             ev.record(root_stream)
         self._grads_ready_event = ev
@@ -278,8 +380,9 @@ class DataParallelEngine:
         for r in range(1, self.world):
             with torch.cuda.device(self.devices[r]):
                 torch.cuda.current_stream().wait_event(ev)
-                for p in self.rparams[r]:
-                    p.grad = None
+                if not graphed:
+                    for p in self.rparams[r]:
+                        p.grad = None
 
 
 def _bind_flat_optimizer(self, optimizer, params):
@@ -330,57 +433,31 @@ class DataParallel(nn.Module):
     def _replica_forward(self, r, x, grad_enabled, autocast_state):
         dev = self.engine.devices[r]
         m = self.engine.modules[r]
-        fwd = m
-        if self._graphed is not None:
-            graphed, eager, shape, dtype = self._graphed[r]
+        graphs = self.engine.graphs
+        if graphs is not None and grad_enabled and m.training and x.shape == graphs[r].shape and x.dtype == graphs[r].dtype:
             # the captured graphs replay one shape in training mode; everything else (eval, ragged last batch) runs eagerly
-            fwd = graphed if (grad_enabled and m.training and x.shape == shape and x.dtype == dtype) else eager
+            return _Replay.apply(graphs[r], x, graphs[r].token)
         with torch.cuda.device(dev), torch.set_grad_enabled(grad_enabled):
             if autocast_state[0]:
                 with torch.autocast("cuda", dtype=autocast_state[1]):
-                    return fwd(x)
-            return fwd(x)
+                    return m(x)
+            return m(x)
 
     def _graph_replicas(self, inputs, autocast_state):
-        """Capture forward + backward of every replica on its device.  ``make_graphed_callables`` runs three warm-up
-        iterations and the capture itself with the sample batch: the BatchNorm buffers they touch are restored afterwards,
-        so graphing does not change the training trajectory."""
+        """Capture forward + backward of every replica on its device (see :class:`_ReplicaGraph`)."""
         eng = self.engine
         from .. import _ext
         for d in eng.devices:
             torch.cuda.synchronize(d)
         n0 = _ext.launches
-        graphed = []
-        for r, m in enumerate(eng.modules):
-            with torch.cuda.device(eng.devices[r]):
-                saved = [b.detach().clone() for b in m.buffers()]
-                eager = m.forward                      # bound method of the un-graphed module
-                sample = inputs[r].detach().clone()
-                # torch.cuda.graph captures on a CLASS-level default stream created on whichever device was current the
-                # first time (device 0): entering it from device r would switch the capture to device 0 while the replica's
-                # kernels run on device r.  Drop it so that this capture creates one on the replica's device.
-                saved_stream = torch.cuda.graph.default_capture_stream
-                torch.cuda.graph.default_capture_stream = None
-                try:
-                    if autocast_state[0]:
-                        with torch.autocast("cuda", dtype=autocast_state[1], cache_enabled=False):
-                            g = torch.cuda.make_graphed_callables(m, (sample,))
-                    else:
-                        g = torch.cuda.make_graphed_callables(m, (sample,))
-                finally:
-                    torch.cuda.graph.default_capture_stream = saved_stream
-                gfwd = g.forward                       # make_graphed_callables patched m.forward: keep both, restore the module
-                m.forward = eager
-                with torch.no_grad():
-                    for b, old in zip(m.buffers(), saved):
-                        b.copy_(old)
-                graphed.append((gfwd, eager, sample.shape, sample.dtype))
+        eng.graphs = [_ReplicaGraph(m, eng.rparams[r], inputs[r], eng.devices[r], autocast_state) for r, m in enumerate(eng.modules)]
+        eng._grad_packs = [eng.grads.make_packs(g.static_grads) for g in eng.graphs]
         for d in eng.devices:
             torch.cuda.synchronize(d)
         # 3 warm-ups + 1 capture ran every native kernel of forward + backward once per replica
         self.graph_launches_per_step = (_ext.launches - n0) // 4
         _ext.launches = n0
-        self._graphed = graphed
+        self._graphed = eng.graphs
 
     def forward(self, x):
         eng = self.engine
@@ -394,7 +471,8 @@ class DataParallel(nn.Module):
                 out = _ArmReduce.apply(eng, out)
             return out
         for m in eng.modules[1:]:
-            m.train(self.module.training)
+            if m.training != self.module.training:       # (walking ~160 submodules of 7 replicas every step is host time)
+                m.train(self.module.training)
         eng.broadcast_values()
         # scatter (copy engines): chunk on dim 0 like torch.nn.parallel.scatter
         chunks = x.chunk(eng.world, dim=0)

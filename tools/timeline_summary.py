@@ -83,30 +83,39 @@ def main():
         print("| %s | %d | %.3f |" % (s, len(es), b / 1e3 / a.steps))
         if b > best:
             main_stream, best = s, b
-    # ---- last step: delimited by the optimizer kernel
-    opt = [e for e in evs if "fused_sgd" in e["name"]]
-    if len(opt) >= 2:
-        lo, hi = opt[-2]["ts"] + opt[-2]["dur"], opt[-1]["ts"] + opt[-1]["dur"]
+    # ---- last complete step: delimited by the metric kernel (exactly one per step, right after the forward pass)
+    marks = [e for e in evs if "metrics_kernel" in e["name"]]
+    if len(marks) >= 2:
+        lo, hi = marks[-2]["ts"], marks[-1]["ts"]
         step = [e for e in evs if lo <= e["ts"] < hi]
-        ms = [e for e in step if e["stream"] == main_stream]
-        print("\nlast step: %.3f ms between optimizer ends; compute stream %s busy %.3f ms, idle %.3f ms" %
-              ((hi - lo) / 1e3, main_stream, union_busy(ms) / 1e3, (hi - lo - union_busy(ms)) / 1e3))
-        gaps = []
-        prev_end = lo
-        for e in ms:
-            if e["ts"] - prev_end > 5.0:
-                gaps.append((e["ts"] - prev_end, prev_end - lo, short(e["name"], 50)))
+        comm_re = re.compile(r"allreduce|broadcast|metrics|barrier|push_kernel|reduce_to_caller|ll_|fused_sgd")
+        comm = [e for e in step if comm_re.search(e["name"])]
+        comp = [e for e in step if not comm_re.search(e["name"])]
+        print("\nlast complete step (metric kernel to metric kernel): %.3f ms; compute kernels busy %.3f ms (union), "
+              "communication / optimizer kernels %.3f ms (sum, overlapped with compute)" %
+              ((hi - lo) / 1e3, union_busy(comp) / 1e3, sum(e["dur"] for e in comm) / 1e3))
+        # the step runs [forward_k+1 ... ] after the marker; backward of step k ends where the last wgrad/dgrad/bn_bwd kernel ends
+        bwd = [e for e in comp if re.search(r"wgrad|dgrad|bwd|backward", e["name"])]
+        if bwd:
+            bwd_end = max(e["ts"] + e["dur"] for e in bwd)
+            after = [e for e in comm if e["ts"] + e["dur"] > bwd_end]
+            tail_end = max([e["ts"] + e["dur"] for e in after] + [bwd_end])
+            print("end of backward compute -> end of the last all-reduce / optimizer kernel (exposed tail): %.1f us" % (tail_end - bwd_end))
+        print("\ncommunication / optimizer kernels of the step (offset from the marker ms, duration us, grid, concurrent compute kernel):")
+        for e in comm:
+            mid = e["ts"] + e["dur"] / 2
+            over = [c for c in comp if c["ts"] <= mid <= c["ts"] + c["dur"]]
+            print("  %7.3f  %8.1f  %-12s %-48s | %s" % ((e["ts"] - lo) / 1e3, e["dur"], e["grid"], short(e["name"], 48),
+                                                        short(over[0]["name"], 40) if over else "(nothing: exposed)"))
+        gaps, prev_end = [], lo
+        for e in sorted(comp, key=lambda x: x["ts"]):
+            if e["ts"] - prev_end > 8.0:
+                gaps.append((e["ts"] - prev_end, (prev_end - lo) / 1e3, short(e["name"], 50)))
             prev_end = max(prev_end, e["ts"] + e["dur"])
         gaps.sort(reverse=True)
-        print("\nlargest idle gaps of the compute stream (us, at offset ms, before kernel):")
-        for g, off, nm in gaps[:12]:
-            print("  %8.1f us  @ %7.3f ms  -> %s" % (g, off / 1e3, nm))
-        print("\ncross-GPU / side-stream kernels in the last step (offset ms, dur us, stream, grid):")
-        for e in step:
-            if e["stream"] != main_stream or re.search(r"allreduce|broadcast|metrics|barrier|push_kernel|reduce_to_caller|ll_", e["name"]):
-                if e["dur"] < 3 and e["stream"] == main_stream:
-                    continue
-                print("  %7.3f  %8.1f  %s  %s  %s" % ((e["ts"] - lo) / 1e3, e["dur"], e["stream"], e["grid"], short(e["name"], 60)))
+        print("\nlargest gaps between compute kernels (us, at offset ms, next kernel):")
+        for g, off, nm in gaps[:8]:
+            print("  %8.1f us  @ %7.3f ms  -> %s" % (g, off, nm))
 
 
 if __name__ == "__main__":
