@@ -897,7 +897,7 @@ __device__ __forceinline__ void stem_quad_dz(const T* __restrict__ dp, const uin
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kBnThreads) stem_bwd_reduce_kernel(const T* __restrict__ dp, const uint2* __restrict__ code,
+__global__ void __launch_bounds__(kBnThreads, 4) stem_bwd_reduce_kernel(const T* __restrict__ dp, const uint2* __restrict__ code,
                                                                      const T* __restrict__ x, const float* __restrict__ saved,
                                                                      float* __restrict__ gsum, int64_t M, int C, PoolGeom g,
                                                                      int rows_per_block) {
@@ -948,7 +948,7 @@ __global__ void __launch_bounds__(kBnThreads) stem_bwd_reduce_kernel(const T* __
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kBnThreads) stem_bwd_apply_kernel(const T* __restrict__ dp, const uint2* __restrict__ code,
+__global__ void __launch_bounds__(kBnThreads, 4) stem_bwd_apply_kernel(const T* __restrict__ dp, const uint2* __restrict__ code,
                                                                     const T* __restrict__ x, const float* __restrict__ saved,
                                                                     const float* __restrict__ gsum, const void* __restrict__ w, int wdt,
                                                                     T* __restrict__ dx, void* __restrict__ dw, void* __restrict__ db,

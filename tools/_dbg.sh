@@ -1,3 +1,4 @@
 mkdir -p gpurun_out; export PYTHONPATH=$PWD
-PTD_PYPROFILE=gpurun_out/c2_dp_pyprofile.txt timeout 240 python bench.py --gpus 8 --steps 20 --warmup 5 --entry dataparallel > gpurun_out/c2_dp.json 2> gpurun_out/c2_dp.err; cat gpurun_out/c2_dp.json; tail -2 gpurun_out/c2_dp.err | cut -c1-300; head -12 gpurun_out/c2_dp_pyprofile.txt
-PTD_TEST_DP_GPUS=8 timeout 200 python -m pytest tests/test_gpu_entrypoints.py -q -k "dataparallel_matches" 2>&1 | tail -3
+timeout 600 python -m pytest tests/test_gpu_fused_paths.py tests/test_gpu_stem.py -q -k "not horovod" 2>&1 | tail -6
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -k regex:stem_ --csv --log-file gpurun_out/d_stem_times.csv python tools/ncu_targets.py stem > gpurun_out/d_stem.log 2>&1; grep -o '"[^"]*stem[^"(]*(\|"gpu__time_duration.sum","ns","[0-9,.]*"' gpurun_out/d_stem_times.csv | paste - - | cut -c1-160
+timeout 300 python bench.py --gpus 1 --steps 30 --warmup 5 > gpurun_out/d_bench1.json 2> gpurun_out/d_bench1.err; grep -o '"ms_per_step": [0-9.]*\|"value": [0-9.]*' gpurun_out/d_bench1.json | head -4; tail -1 gpurun_out/d_bench1.err | cut -c1-200
