@@ -21,6 +21,9 @@ WANT = {
     "barrier": r"barrier_kernel",
     "fused_sgd_flat_bf16": r"fused_sgd_flat_kernelI13__nv_bfloat16S1_Lb1E",
     "gemm_bnstats_tcgen05_n256": r"gemm_bnstats_persistent_kernelILi256E",
+    "oneshot_allreduce_bf16_nvls": r"oneshot_allreduce_kernelI13__nv_bfloat16Lb1E",
+    "stem_im2col": r"stem_im2col_kernelE",
+    "stem_bwd_reduce_bf16": r"stem_bwd_reduce_kernelI13__nv_bfloat16E",
     "stem_fwd_bf16": r"stem_fwd_kernelI13__nv_bfloat16E",
     "stem_bwd_apply_bf16": r"stem_bwd_apply_kernelI13__nv_bfloat16E",
     "bn_stats_bf16": r"bn_stats_kernelI13__nv_bfloat16E",
