@@ -286,3 +286,44 @@ def test_launch_helpers(monkeypatch):
     monkeypatch.setenv("WORLD_SIZE", "4")
     monkeypatch.setenv("LOCAL_RANK", "3")
     assert launch.torchrun_env() == (3, 3, 4)
+
+
+def test_compute_buckets_tail_bucket_is_split_off():
+    """The last bucket is the only exposed one: the trailing tensors (up to the tail cap) get their own small bucket."""
+    from pytorch_distributed_b200.parallel import plan as P
+    numels = [1000, 2_000_000, 3_000_000, 4_000_000, 100_000, 50_000, 30_000, 9_000]
+    plain = P.compute_buckets(numels, 2, 8 << 20, 1 << 20, 256)
+    tail = P.compute_buckets(numels, 2, 8 << 20, 1 << 20, 256, tail_cap_bytes=256 << 10)
+    flat = lambda bs: [i for b in bs for i in b]          # noqa: E731
+    assert flat(plain) == flat(tail) == list(range(len(numels)))              # order preserved, nothing lost
+    assert tail[-1] == [5, 6, 7]                                              # 100 + 60 + 18 KB fit in 256 KiB, the next 200 KB do not
+    assert sum(numels[i] for i in tail[-1]) * 2 <= (256 << 10) and len(tail) >= len(plain)
+    assert P.compute_buckets([10, 20], 4, 1 << 20, None, 256, tail_cap_bytes=4) == [[0, 1]]      # nothing fits the cap: unchanged
+    # every bucket respects the tensor limit
+    many = P.compute_buckets([8] * 1000, 2, 1 << 30, None, 256, tail_cap_bytes=1 << 10)
+    assert all(len(b) <= 256 for b in many) and flat(many) == list(range(1000))
+
+
+def test_choose_grid_granularity():
+    from pytorch_distributed_b200.parallel import plan as P
+    assert P.choose_grid(1 << 20, 2, 32) == 8                       # 2 MiB at 256 KiB per CTA
+    assert P.choose_grid(1 << 20, 2, 32, 32 << 10) == 32            # tail bucket: 32 KiB per CTA, capped by max_ctas
+    assert P.choose_grid(100, 2, 32, 16 << 10) == 1
+    lay = P.build_layout([1000, 3000, 77], world=8, grid=P.choose_grid(4096 + 64, 2, 32, 1 << 10))
+    assert lay.block_elems % (8 * 8) == 0 and lay.region_elems >= 1000 + 3000 + 77
+
+
+def test_reference_install_manifest(tmp_path, monkeypatch):
+    """baseline/install_reference.py: the copy is verified against the sha256 manifest; a tampered file is reported."""
+    import shutil
+    from baseline import install_reference as inst
+    if not os.path.exists("/root/reference/distributed.py"):
+        pytest.skip("reference tree not mounted")
+    monkeypatch.setattr(inst, "REF_DIR", str(tmp_path / "_ref"))
+    msg = inst.install(force=True)
+    assert "installed" in msg and inst.verify(str(tmp_path / "_ref")) == []
+    with open(tmp_path / "_ref" / "distributed.py", "a") as f:
+        f.write("# tampered\n")
+    assert inst.verify(str(tmp_path / "_ref")) == ["distributed.py"]
+    shutil.rmtree(tmp_path / "_ref")
+    assert len(inst.verify(str(tmp_path / "_ref"))) == len(inst.MANIFEST)
