@@ -80,6 +80,10 @@ class FusedSGD(Optimizer):
     def _prepare_overlap(self) -> None:
         """First bucket of a backward pass, on the compute stream: decide whether this step is applied bucket by bucket
         and push the hyper-parameters to the device before the side stream forks off."""
+        if self._ov_active and self._ov_applied:
+            raise RuntimeError("FusedSGD(overlap_backward=True): a second backward pass started before step() - the update of the "
+                               "previous pass has already been applied bucket by bucket; use overlap_backward=False "
+                               "(--no-overlap-optimizer) for gradient accumulation")
         self._ov_applied = 0
         self._ov_active = self._flat is not None and self._amp is None
         if self._ov_active:
