@@ -102,6 +102,20 @@ class Compression:
         wire = "bf16"
 
 
+# reduction ops of horovod's `op=` argument (Adasum needs its own kernel and is not provided)
+Average, Sum, Adasum = "average", "sum", "adasum"
+
+
+def _op_average(op, average: bool) -> bool:
+    if op is None:
+        return bool(average)
+    if op == Average:
+        return True
+    if op == Sum:
+        return False
+    raise NotImplementedError("hvd op %r is not supported (available: hvd.Average, hvd.Sum)" % (op,))
+
+
 # ---------------------------------------------------------------------- tensor collectives
 def _wire_for(t: torch.Tensor, compression) -> Optional[str]:
     w = getattr(compression, "wire", None)
@@ -110,7 +124,8 @@ def _wire_for(t: torch.Tensor, compression) -> Optional[str]:
     return w
 
 
-def allreduce_(tensor: torch.Tensor, average: bool = True, name: Optional[str] = None, compression=Compression.none) -> torch.Tensor:
+def allreduce_(tensor: torch.Tensor, average: bool = True, name: Optional[str] = None, compression=Compression.none, op=None) -> torch.Tensor:
+    average = _op_average(op, average)
     c = _state["comm"]
     if c is None or c.world == 1:
         return tensor
@@ -121,8 +136,37 @@ def allreduce_(tensor: torch.Tensor, average: bool = True, name: Optional[str] =
     return tensor
 
 
-def allreduce(tensor: torch.Tensor, average: bool = True, name: Optional[str] = None, compression=Compression.none) -> torch.Tensor:
-    return allreduce_(tensor.clone(), average=average, name=name, compression=compression)
+def allreduce(tensor: torch.Tensor, average: bool = True, name: Optional[str] = None, compression=Compression.none, op=None) -> torch.Tensor:
+    return allreduce_(tensor.clone(), average=average, name=name, compression=compression, op=op)
+
+
+def allgather(tensor: torch.Tensor, name: Optional[str] = None) -> torch.Tensor:
+    """Concatenation of every rank's tensor along dim 0 (first dimensions may differ, like horovod).  Not on any hot path of
+    the reference scripts: served by the library collective of the control plane."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return tensor.clone()
+    sizes = [torch.zeros(1, dtype=torch.int64, device=tensor.device) for _ in range(size())]
+    dist.all_gather(sizes, torch.tensor([tensor.size(0)], dtype=torch.int64, device=tensor.device))
+    sizes = [int(s.item()) for s in sizes]
+    mx = max(sizes)
+    pad = tensor if tensor.size(0) == mx else torch.cat([tensor, tensor.new_zeros((mx - tensor.size(0),) + tuple(tensor.shape[1:]))])
+    outs = [torch.empty_like(pad) for _ in sizes]
+    dist.all_gather(outs, pad.contiguous())
+    return torch.cat([o[:n] for o, n in zip(outs, sizes)])
+
+
+def broadcast_object(obj, root_rank: int = 0, name: Optional[str] = None):
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return obj
+    box = [obj]
+    dist.broadcast_object_list(box, src=root_rank)
+    return box[0]
+
+
+def barrier() -> None:
+    c = _state["comm"]
+    if c is not None and c.world > 1:
+        c.barrier()
 
 
 def allreduce_async_(tensor: torch.Tensor, average: bool = True, name: Optional[str] = None) -> int:
@@ -493,6 +537,8 @@ def DistributedOptimizer(optimizer, named_parameters=None, compression=Compressi
     """
     if not _state["init"]:
         init()
+    if not _op_average(op, True):
+        raise NotImplementedError("DistributedOptimizer(op=hvd.Sum): gradients are averaged (horovod's default); scale the loss instead")
     comm = _state["comm"]
     if named_parameters is None:
         named_parameters = [("param.%d" % i, p) for i, p in enumerate(p for g in optimizer.param_groups for p in g["params"])]

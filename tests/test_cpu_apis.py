@@ -21,6 +21,12 @@ out = hvd.allreduce(t, name="barrier")                 # out-of-place, averaged 
 assert torch.allclose(out, torch.full((5,), 1.5)) and torch.allclose(t, torch.full((5,), float(r + 1)))
 hvd.allreduce_(t, average=False)
 assert torch.allclose(t, torch.full((5,), 3.0))
+assert torch.allclose(hvd.allreduce(torch.full((2,), float(r + 1)), op=hvd.Sum), torch.full((2,), 3.0))
+assert torch.allclose(hvd.allreduce(torch.full((2,), float(r + 1)), op=hvd.Average), torch.full((2,), 1.5))
+g = hvd.allgather(torch.full((r + 1, 2), float(r)))                      # ragged first dimension: 1 row from rank 0, 2 from rank 1
+assert g.shape == (3, 2) and g[:, 0].tolist() == [0.0, 1.0, 1.0]
+assert hvd.broadcast_object({"lr": 0.1 * (r + 1)}, root_rank=1) == {"lr": 0.2}
+hvd.barrier()
 h = hvd.allreduce_async_(torch.full((3,), float(r)), average=True)
 assert hvd.poll(h) in (True, False)
 assert torch.allclose(hvd.synchronize(h), torch.full((3,), 0.5))
@@ -140,6 +146,14 @@ def test_apex_namespace_surface():
     assert callable(amp.initialize) and callable(amp.scale_loss) and callable(amp.master_params)
     assert callable(amp.state_dict) and callable(amp.load_state_dict)
     assert DistributedDataParallel.__name__ == "DistributedDataParallel" and Reducer is not None and apex.amp is amp
+    from pytorch_distributed_b200.apex.optimizers import FusedSGD
+    from pytorch_distributed_b200.ops.fused_sgd import FusedSGD as Own
+    assert FusedSGD is Own
+    import pytest as _pt
+    lin = torch.nn.Linear(2, 2)
+    for bad in (dict(num_allreduce_streams=2), dict(allreduce_trigger_params=[lin.weight]), dict(shared_param=True)):
+        with _pt.raises((NotImplementedError, ValueError)):
+            DistributedDataParallel(lin, comm="gloo", **bad)
 
 
 def test_amp_o2_casts_in_place_and_keeps_fp32_masters_cpu():
