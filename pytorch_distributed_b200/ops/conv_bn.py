@@ -8,9 +8,8 @@ Falls back to ``F.conv2d`` + :func:`bn_act` whenever the fast path does not appl
 from __future__ import annotations
 
 import torch
-import torch.nn.functional as F
 
-from .bn_act import _BnActFn, _can_fuse, bn_act, workspace
+from .bn_act import _BnActFn, _can_fuse, workspace
 
 
 class _Conv1x1Stats(torch.autograd.Function):

@@ -28,7 +28,7 @@ import torch.nn as nn
 
 from . import plan as P
 from ..utils.tensors import is_dense
-from .comm import KIND_ONE_SHOT, KIND_TWO_SHOT, FusedCommunicator, TorchCommunicator, make_communicator
+from .comm import KIND_ONE_SHOT, KIND_TWO_SHOT, FusedCommunicator, make_communicator
 
 _WIRE_OF = {torch.float32: "fp32", torch.bfloat16: "bf16", torch.float16: "fp16"}
 

@@ -24,7 +24,6 @@ from __future__ import annotations
 
 import copy
 import os
-import threading
 import weakref
 from concurrent.futures import ThreadPoolExecutor
 from typing import List, Optional
