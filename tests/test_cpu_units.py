@@ -327,3 +327,30 @@ def test_reference_install_manifest(tmp_path, monkeypatch):
     assert inst.verify(str(tmp_path / "_ref")) == ["distributed.py"]
     shutil.rmtree(tmp_path / "_ref")
     assert len(inst.verify(str(tmp_path / "_ref"))) == len(inst.MANIFEST)
+
+
+def test_timeline_summary_tool_on_a_synthetic_trace(tmp_path):
+    """tools/timeline_summary.py: step delimiting by the metric kernel, exposed-tail computation, kernel table."""
+    import json
+    import subprocess
+    import sys
+    evs = []
+    t = 0.0
+    for step in range(3):
+        evs.append({"ph": "X", "cat": "kernel", "name": "void ptd::metrics_kernel<bf16>(x)", "ts": t, "dur": 20.0, "args": {"stream": 9, "grid": [1, 1, 1]}})
+        for k in range(5):
+            evs.append({"ph": "X", "cat": "kernel", "name": "cudnn_wgrad_kernel_%d" % k, "ts": t + 30 + k * 100, "dur": 90.0, "args": {"stream": 7, "grid": [100, 1, 1]}})
+        evs.append({"ph": "X", "cat": "kernel", "name": "void ptd::fused_allreduce_kernel<bf16, true>(x)", "ts": t + 300, "dur": 50.0, "args": {"stream": 9, "grid": [32, 1, 1]}})
+        # the tail bucket starts after the last backward kernel ended (t + 520): 25 us of exposed communication + optimizer
+        evs.append({"ph": "X", "cat": "kernel", "name": "void ptd::fused_allreduce_kernel<bf16, true>(x)", "ts": t + 522, "dur": 18.0, "args": {"stream": 9, "grid": [29, 1, 1]}})
+        evs.append({"ph": "X", "cat": "kernel", "name": "void ptd::fused_sgd_flat_kernel<bf16>(x)", "ts": t + 540, "dur": 5.0, "args": {"stream": 9, "grid": [200, 1, 1]}})
+        evs.append({"ph": "X", "cat": "kernel", "name": "forward_kernel", "ts": t + 550, "dur": 400.0, "args": {"stream": 7, "grid": [100, 1, 1]}})
+        t += 1000.0
+    path = tmp_path / "tl.json"
+    path.write_text(json.dumps({"traceEvents": evs}))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "timeline_summary.py"), str(path), "--top", "5"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert "last complete step (metric kernel to metric kernel): 1.000 ms" in out.stdout
+    assert "exposed tail): 25.0 us" in out.stdout
+    assert "fused_allreduce_kernel" in out.stdout and "(nothing: exposed)" in out.stdout
